@@ -1,0 +1,122 @@
+/*
+ * jenga_b200 — C ABI of the B200-native AttenCarve hot path.
+ *
+ * Drop-in boundary for the one path of dvlab-research/Jenga that BASELINE.json names:
+ * gilbert token reordering, block scoring/selection and the 128x128 block-sparse
+ * self-attention (RMSNorm + RoPE prologue), as hand-written sm_100a CUDA.
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; device pointers unless the name says "host";
+ *   - returns 0 on success, a negative JENGA_E_* code otherwise; never throws;
+ *   - never allocates device memory (callers pass workspaces sized by the *_bytes queries);
+ *   - never synchronises: work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     JENGA_E_CUDA.
+ *
+ * "ref:" comments cite the reference interface each entry point replaces
+ * (paths relative to the Jenga repository root).
+ */
+#ifndef JENGA_B200_H_
+#define JENGA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JENGA_B200_ABI_VERSION 1
+
+enum {
+  JENGA_OK = 0,
+  JENGA_E_INVALID = -1,     /* bad argument (shape, stride, alignment, dtype)        */
+  JENGA_E_UNSUPPORTED = -2, /* valid in the reference but not built here (e.g. D!=128) */
+  JENGA_E_CUDA = -3,        /* CUDA runtime / driver error; see jenga_last_error()   */
+  JENGA_E_WORKSPACE = -4    /* workspace too small                                   */
+};
+
+enum { JENGA_BF16 = 0, JENGA_F16 = 1, JENGA_F32 = 2 };
+
+int jenga_abi_version(void);
+/* Thread-local, human-readable description of the last non-zero return. */
+const char* jenga_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-1..a-3) gilbert curve permutations and block adjacency — host, once per resolution.
+ * ref: gilbert.py:442 gilbert_mapping, :332 sliced_gilbert_mapping,
+ *      :597 gilbert_block_neighbor_mapping, :679 sliced_gilbert_block_neighbor_mapping.
+ * linear index = z*h*w + y*w + x over a (t,h,w) latent grid.  Outputs are host arrays of
+ * t*h*w int64 (permutations) and nb*nb bytes (0/1), nb = ceil(t*h*w / block).
+ * sliced != 0 selects the per-frame ("sliced") curve used by Wan2.1.
+ * ---------------------------------------------------------------------------------------- */
+int jenga_gilbert_mapping_host(int t, int h, int w, int sliced, int64_t* linear_to_hilbert,
+                               int64_t* hilbert_to_linear);
+int jenga_gilbert_block_neighbors_host(int t, int h, int w, int block, int sliced,
+                                       uint8_t* neighbors /* [nb*nb] */);
+/* Scalar curve index of one voxel.  ref: gilbert.py:12 gilbert_xyz2d. */
+int64_t jenga_gilbert_xyz2d(int x, int y, int z, int width, int height, int depth);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-4) token gather / scatter along the curve.
+ * ref: jenga_hyvideo.py:116-118,226; jenga_wan.py:559,655 (x[:, hilbert_order], x[:, l2h]).
+ * dst[b, i, :] = src[b, index[i], :] for i < n_index; rows are `row_bytes` contiguous bytes
+ * (multiple of 16), batch strides in bytes.  index is int64 on the device.
+ * ---------------------------------------------------------------------------------------- */
+int jenga_gather_rows(const void* src, void* dst, const int64_t* index, int64_t n_index,
+                      int64_t n_src_rows, int64_t row_bytes, int batch, int64_t src_batch_stride,
+                      int64_t dst_batch_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-9, a-10) carved attention forward.
+ * ref: hyvideo/modules/attention_block_triton_diffres.py:38-136 (kernel), :139-196 (launcher),
+ *      :371-380 (text rows through flash_attn_func); wan/... and hyvideo_i2v/... twins.
+ *
+ * q,k,v,out are [B, S, H, D] with D contiguous (element strides given for b, s, h).
+ * Query blocks of 128 rows come in two classes, both written to `out` by one launch:
+ *   sparse  : q-blocks [0, nq_sparse)  — key blocks from `mask_bits` (ref one-hot kernel);
+ *   dense   : q-blocks [nq_sparse, nq_sparse + nq_dense) — every key block (ref text rows).
+ * mask_bits: [B*H, nq_sparse, mask_words] uint32, bit j of word w set <=> key block 32*w+j
+ * is attended (ascending order, like the reference loop over the one-hot row).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct JengaAttnArgs {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t dtype; /* JENGA_BF16 | JENGA_F16 */
+  int32_t batch, heads, head_dim;
+  int64_t q_rows, kv_rows;                           /* S of q/out and of k/v            */
+  int64_t q_stride_b, q_stride_s, q_stride_h;        /* element strides                 */
+  int64_t k_stride_b, k_stride_s, k_stride_h;
+  int64_t v_stride_b, v_stride_s, v_stride_h;
+  int64_t o_stride_b, o_stride_s, o_stride_h;
+  int32_t nq_sparse, nq_dense;
+  const uint32_t* mask_bits;
+  int32_t mask_words;
+  /* sparse class (ref Triton kernel): Q is pre-scaled by sm_scale*log2(e) and re-rounded to
+   * the input dtype (:87-88), text_amp is added in log2 units to key blocks >=
+   * text_block_start (:113-114), key columns >= kv_limit_sparse are masked (:117-118),
+   * query rows >= q_limit_sparse produce zeros (:136 + zeros_like :156). */
+  float sm_scale;
+  float text_amp;
+  int32_t text_block_start;
+  int64_t kv_limit_sparse;
+  int64_t q_limit_sparse;
+  /* dense class (ref flash_attn_func on the text rows): plain softmax(q k^T sm_scale) v over
+   * key columns < kv_limit_dense. */
+  int64_t kv_limit_dense;
+  int32_t* err_flag; /* device int, may be NULL: set non-zero by in-kernel watchdogs */
+} JengaAttnArgs;
+
+int jenga_carved_attn_fwd(const JengaAttnArgs* args, void* stream);
+
+/* One-hot bool mask [BH, nq, nb] (ref: the tensor returned by
+ * _build_block_index_with_importance_optimized, attention_block_triton_diffres.py:198-295)
+ * -> packed bit rows [BH, nq, mask_words]. */
+int jenga_mask_onehot_to_bits(const uint8_t* onehot, uint32_t* bits, int64_t rows, int32_t nb,
+                              int32_t mask_words, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JENGA_B200_H_ */

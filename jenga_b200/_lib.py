@@ -1,0 +1,74 @@
+"""ctypes binding of libjenga_b200.so (the C-ABI declared in include/jenga_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, importing this module
+raises, and every compute entry point returns an error code without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_C" / "libjenga_b200.so"
+
+JENGA_BF16, JENGA_F16, JENGA_F32 = 0, 1, 2
+
+
+class JengaError(RuntimeError):
+    pass
+
+
+class JengaAttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("dtype", C.c_int32), ("batch", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("q_rows", C.c_int64), ("kv_rows", C.c_int64),
+        ("q_stride_b", C.c_int64), ("q_stride_s", C.c_int64), ("q_stride_h", C.c_int64),
+        ("k_stride_b", C.c_int64), ("k_stride_s", C.c_int64), ("k_stride_h", C.c_int64),
+        ("v_stride_b", C.c_int64), ("v_stride_s", C.c_int64), ("v_stride_h", C.c_int64),
+        ("o_stride_b", C.c_int64), ("o_stride_s", C.c_int64), ("o_stride_h", C.c_int64),
+        ("nq_sparse", C.c_int32), ("nq_dense", C.c_int32),
+        ("mask_bits", C.c_void_p), ("mask_words", C.c_int32),
+        ("sm_scale", C.c_float), ("text_amp", C.c_float), ("text_block_start", C.c_int32),
+        ("kv_limit_sparse", C.c_int64), ("q_limit_sparse", C.c_int64),
+        ("kv_limit_dense", C.c_int64),
+        ("err_flag", C.c_void_p),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise JengaError(
+            f"{LIB_PATH} is missing: build it with `python -m jenga_b200.build` "
+            "(or __graft_entry__.build()); jenga_b200 has no fallback path")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.jenga_abi_version.restype = C.c_int
+    lib.jenga_last_error.restype = C.c_char_p
+    lib.jenga_carved_attn_fwd.argtypes = [C.POINTER(JengaAttnArgs), C.c_void_p]
+    lib.jenga_carved_attn_fwd.restype = C.c_int
+    lib.jenga_mask_onehot_to_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                              C.c_int32, C.c_void_p]
+    lib.jenga_mask_onehot_to_bits.restype = C.c_int
+    lib.jenga_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    lib.jenga_gather_rows.restype = C.c_int
+    lib.jenga_gilbert_mapping_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_void_p]
+    lib.jenga_gilbert_mapping_host.restype = C.c_int
+    lib.jenga_gilbert_block_neighbors_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int,
+                                                       C.c_int, C.c_void_p]
+    lib.jenga_gilbert_block_neighbors_host.restype = C.c_int
+    lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
+    lib.jenga_gilbert_xyz2d.restype = C.c_int64
+    if lib.jenga_abi_version() != 1:
+        raise JengaError("libjenga_b200.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.jenga_last_error().decode(errors="replace")
+        raise JengaError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,142 @@
+// extern "C" surface of libjenga_b200.so (declared in include/jenga_b200.h) plus the small
+// bandwidth-bound kernels that do not deserve their own translation unit.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "jenga_internal.h"
+
+namespace jenga {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int set_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return JENGA_E_CUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn resolve_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, void* base,
+                      const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const cuuint32_t* elem_strides,
+                      CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion l2,
+                      CUtensorMapFloatOOBfill oob) {
+  EncodeTiledFn fn = resolve_encode();
+  if (!fn) return set_error(JENGA_E_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const CUresult r = fn(map, dt, rank, base, dims, strides_bytes, box, elem_strides, il, sw, l2, oob);
+  if (r != CUDA_SUCCESS)
+    return set_error(JENGA_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return JENGA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// gather_rows: dst[b, i, :] = src[b, index[i], :]     (HBM-bound; 16-byte vectors)
+// One warp per destination row chunk; index loaded once per row, broadcast by shuffle.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                   const long long* __restrict__ index, long long n_index, long long n_src_rows,
+                   int vec_per_row, long long src_batch_vec, long long dst_batch_vec) {
+  const int b = blockIdx.y;
+  const uint4* s = src + b * src_batch_vec;
+  uint4* d = dst + b * dst_batch_vec;
+  const long long total = n_index * vec_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / vec_per_row;
+    const int col = static_cast<int>(i - row * vec_per_row);
+    long long srow = __ldg(index + row);
+    if (srow < 0) srow += n_src_rows;  // torch-style negative index
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (srow >= 0 && srow < n_src_rows) v = __ldg(s + srow * vec_per_row + col);
+    d[i] = v;
+  }
+}
+
+// one-hot bytes [rows, nb] -> bit rows [rows, words]
+__global__ void __launch_bounds__(256)
+onehot_to_bits_kernel(const uint8_t* __restrict__ onehot, uint32_t* __restrict__ bits,
+                      long long rows, int nb, int words) {
+  const long long gw = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = rows * words;
+  if (gw >= total) return;
+  const long long row = gw / words;
+  const int w = static_cast<int>(gw - row * words);
+  const int col = w * 32 + lane;
+  const bool on = col < nb && onehot[row * nb + col] != 0;
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) bits[gw] = word;
+}
+
+}  // namespace jenga
+
+using namespace jenga;
+
+extern "C" int jenga_abi_version(void) { return JENGA_B200_ABI_VERSION; }
+extern "C" const char* jenga_last_error(void) { return g_err; }
+
+extern "C" int jenga_carved_attn_fwd(const JengaAttnArgs* args, void* stream) {
+  return carved_attn_fwd_impl(args, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int jenga_gather_rows(const void* src, void* dst, const int64_t* index, int64_t n_index,
+                                 int64_t n_src_rows, int64_t row_bytes, int batch,
+                                 int64_t src_batch_stride, int64_t dst_batch_stride, void* stream) {
+  if (!src || !dst || !index) return set_error(JENGA_E_INVALID, "gather_rows: null pointer");
+  if (n_index < 0 || n_src_rows <= 0 || batch <= 0)
+    return set_error(JENGA_E_INVALID, "gather_rows: bad sizes");
+  if (row_bytes <= 0 || row_bytes % 16 || src_batch_stride % 16 || dst_batch_stride % 16 ||
+      reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(dst) % 16)
+    return set_error(JENGA_E_INVALID, "gather_rows: rows must be 16-byte multiples and aligned");
+  if (n_index == 0) return JENGA_OK;
+  const int vec = static_cast<int>(row_bytes / 16);
+  const long long total = n_index * vec;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 148ll * 8 * 4;  // a few waves of 8 CTAs/SM; grid-stride beyond that
+  if (blocks > cap) blocks = cap;
+  dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(batch));
+  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst),
+      reinterpret_cast<const long long*>(index), n_index, n_src_rows, vec, src_batch_stride / 16,
+      dst_batch_stride / 16);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "gather_rows launch");
+}
+
+extern "C" int jenga_mask_onehot_to_bits(const uint8_t* onehot, uint32_t* bits, int64_t rows,
+                                         int32_t nb, int32_t mask_words, void* stream) {
+  if (!onehot || !bits) return set_error(JENGA_E_INVALID, "onehot_to_bits: null pointer");
+  if (rows <= 0 || nb <= 0 || mask_words * 32 < nb)
+    return set_error(JENGA_E_INVALID, "onehot_to_bits: bad sizes");
+  const long long warps = rows * mask_words;
+  const long long blocks = (warps * 32 + 255) / 256;
+  onehot_to_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      onehot, bits, rows, nb, mask_words);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "onehot_to_bits launch");
+}

@@ -1,0 +1,468 @@
+// Carved (block-sparse) flash-attention forward for sm_100a.
+//
+// Replaces the reference's Triton one-hot kernel
+//   hyvideo/modules/attention_block_triton_diffres.py:38-136 (+ launcher :139-196)
+// and its text-row flash_attn_func call (:371-380) with ONE launch.
+//
+// Work decomposition: one CTA per (batch*head, 128-row query block); 192 threads:
+//   warp 0      TMA producer      Q once, then one K tile and one V tile per live key block
+//   warp 1      tcgen05 issuer    S = Q~ K^T (SS), O += P V (TS, P read from TMEM); owns TMEM
+//   warps 2..5  softmax           one query row per thread: tcgen05.ld S -> online softmax in
+//                                 base 2 -> P as packed 16-bit back into TMEM; lazy O rescale;
+//                                 final O / l -> global
+// Two CTAs are co-resident per SM (256 TMEM columns and ~100 KB shared memory each) so one
+// CTA's softmax overlaps the other CTA's MMAs.
+//
+// HBM/L2 layout: q,k,v stay in the caller's [B,S,H,D] layout; TMA boxes are {64 d, 128 rows}
+// with 128-byte swizzle, i.e. two 16 KB half tiles per 128x128 tile.  K half tiles are
+// K-major UMMA operands, V half tiles are MN-major UMMA operands (no transpose anywhere).
+// CTAs are numbered head-major so that all CTAs in flight read the same head's K/V (59 MB at
+// 115K tokens) out of L2.
+#include "sm100_ptx.cuh"
+#include "jenga_internal.h"
+
+namespace jenga {
+
+namespace {
+
+constexpr int kBlock = 128;           // rows per q block == keys per kv block
+constexpr int kHeadDim = 128;
+constexpr int kThreads = 192;
+constexpr int kHalfTileBytes = kBlock * 64 * 2;  // 16 KB: 128 rows x 64 elems x 2 B
+constexpr int kTileBytes = 2 * kHalfTileBytes;   // 32 KB
+constexpr int kMaxMaskWords = 256;               // up to 8192 key blocks (1M tokens)
+constexpr uint32_t kTmemCols = 256;              // S/P: [0,128)  O: [128,256)
+
+// shared-memory carve-up (offsets from the 1024-aligned base)
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kTileBytes;
+constexpr int kOffV = kOffK + kTileBytes;
+constexpr int kOffBars = kOffV + kTileBytes;  // 8 mbarriers + tmem slot
+constexpr int kOffMask = kOffBars + 128;
+constexpr int kSmemBytes = 1024 /*align slack*/ + kOffMask + kMaxMaskWords * 4;
+
+enum BarId { Q_FULL = 0, Q_READY, K_FULL, K_EMPTY, V_FULL, S_FULL, P_FULL, PV_DONE, NUM_BARS };
+
+struct KernelParams {
+  int heads;
+  int nq_sparse, nq_dense;
+  int nb_kv;
+  int mask_words;
+  int text_block_start;
+  long long q_rows;           // rows present in q / out
+  long long q_limit_sparse;   // sparse rows >= this produce zeros
+  long long kv_limit_sparse;  // key columns >= this are masked for sparse q blocks
+  long long kv_limit_dense;   // ... for dense q blocks
+  float qk_scale;             // sm_scale * log2(e)
+  float text_amp;
+  const uint32_t* mask_bits;
+  void* out;
+  long long o_stride_b, o_stride_s, o_stride_h;  // elements
+  int* err_flag;
+};
+
+// Walks the set bits of the row mask in ascending key-block order.
+struct BlockWalker {
+  const uint32_t* words;
+  int nwords;
+  int w;
+  uint32_t bits;
+  __device__ BlockWalker(const uint32_t* m, int n) : words(m), nwords(n), w(0), bits(n ? m[0] : 0) {}
+  __device__ int next() {  // -1 when exhausted
+    while (bits == 0) {
+      if (++w >= nwords) return -1;
+      bits = words[w];
+    }
+    const int j = __ffs(bits) - 1;
+    bits &= bits - 1;
+    return w * 32 + j;
+  }
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 2)
+carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
+                       const __grid_constant__ CUtensorMap tm_k,
+                       const __grid_constant__ CUtensorMap tm_v, const KernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem + kOffQ;
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + kOffMask);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- which tile is this CTA?  head-major; within a head the (long) dense blocks first ----
+  const int per_bh = p.nq_sparse + p.nq_dense;
+  const int bh = blockIdx.x / per_bh;
+  const int local = blockIdx.x - bh * per_bh;
+  const bool dense = local < p.nq_dense;
+  const int qb = dense ? p.nq_sparse + local : local - p.nq_dense;
+  const int b = bh / p.heads;
+  const int h = bh - b * p.heads;
+  const long long q_row0 = static_cast<long long>(qb) * kBlock;
+  const long long kv_limit = dense ? p.kv_limit_dense : p.kv_limit_sparse;
+  // ref :59-61 — a sparse q block entirely past seqlen is skipped (its rows stay zero)
+  const bool skip_all = (!dense && q_row0 >= p.q_limit_sparse);
+
+  // ---- stage the row mask in shared memory ----
+  const int nwords = p.mask_words;
+  for (int w = threadIdx.x; w < nwords; w += kThreads) {
+    uint32_t bits;
+    if (skip_all) {
+      bits = 0;
+    } else if (dense) {
+      const int lo = w * 32;
+      const int rem = p.nb_kv - lo;
+      bits = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+    } else {
+      bits = p.mask_bits[(static_cast<size_t>(bh) * p.nq_sparse + qb) * nwords + w];
+      // never walk past the key blocks that exist
+      const int rem = p.nb_kv - w * 32;
+      if (rem < 32) bits &= rem > 0 ? ((1u << rem) - 1u) : 0u;
+    }
+    s_mask[w] = bits;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(&bars[Q_FULL], 1);
+    mbar_init(&bars[Q_READY], 128);
+    mbar_init(&bars[K_FULL], 1);
+    mbar_init(&bars[K_EMPTY], 1);
+    mbar_init(&bars[V_FULL], 1);
+    mbar_init(&bars[S_FULL], 1);
+    mbar_init(&bars[P_FULL], 128);
+    mbar_init(&bars[PV_DONE], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // fp32 S, later packed P in columns [0,64)
+  const uint32_t tmem_O = tmem_base + 128;  // fp32 O accumulator
+
+  int n_tiles = 0;
+  for (int w = 0; w < nwords; ++w) n_tiles += __popc(s_mask[w]);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0 && n_tiles > 0) {
+      mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
+      tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, static_cast<int>(q_row0), h, b);
+      tma_load_4d(sQ + kHalfTileBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b);
+      BlockWalker it(s_mask, nwords);
+      int j = 0;
+      for (int blk = it.next(); blk >= 0; blk = it.next(), ++j) {
+        const int row0 = blk * kBlock;
+        const uint32_t par = (j & 1) ^ 1;
+        mbar_wait(&bars[K_EMPTY], par, p.err_flag);
+        mbar_arrive_expect_tx(&bars[K_FULL], kTileBytes);
+        tma_load_4d(sK, &tm_k, &bars[K_FULL], 0, row0, h, b);
+        tma_load_4d(sK + kHalfTileBytes, &tm_k, &bars[K_FULL], 64, row0, h, b);
+        mbar_wait(&bars[PV_DONE], par, p.err_flag);  // V slot free == PV of tile j-1 retired
+        mbar_arrive_expect_tx(&bars[V_FULL], kTileBytes);
+        tma_load_4d(sV, &tm_v, &bars[V_FULL], 0, row0, h, b);
+        tma_load_4d(sV + kHalfTileBytes, &tm_v, &bars[V_FULL], 64, row0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== tcgen05 issuer ===============================
+    if (lane == 0 && n_tiles > 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, /*b_mn_major=*/false, 128, 128);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, /*b_mn_major=*/true, 128, 128);
+      // K-major SW128 operands (Q, K): 8-row groups are 1024 B apart; LBO unused (=16 B)
+      const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 16, 1024, UMMA_LAYOUT_SW128);
+      // MN-major SW128 operand (V): 64-wide d chunks are one half tile (16 KB) apart (LBO),
+      // 8-key groups are 1024 B apart (SBO)
+      const uint64_t v_desc =
+          umma_smem_desc(smem_u32(sV), kHalfTileBytes, 1024, UMMA_LAYOUT_SW128);
+
+      mbar_wait(&bars[Q_READY], 0, p.err_flag);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t par = j & 1;
+        mbar_wait(&bars[K_FULL], par, p.err_flag);
+        if (j > 0) mbar_wait(&bars[PV_DONE], par ^ 1, p.err_flag);  // S/P columns free again
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+          // 16 d-elements = 32 B inside the 128-B swizzle row; second d-half is +16 KB
+          const uint64_t off = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kHalfTileBytes) >> 4);
+          umma_ss(tmem_S, q_desc + off, k_desc + off, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&bars[K_EMPTY]);
+        umma_commit(&bars[S_FULL]);
+
+        mbar_wait(&bars[V_FULL], par, p.err_flag);
+        mbar_wait(&bars[P_FULL], par, p.err_flag);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBlock / 16; ++kk) {
+          // 16 keys = 16 rows x 128 B inside each V half tile; P advances 8 packed columns
+          const uint64_t off = static_cast<uint64_t>((kk * 16 * 128) >> 4);
+          umma_ts(tmem_O, tmem_S + kk * 8, v_desc + off, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars[PV_DONE]);
+      }
+    }
+  } else {
+    // =============================== softmax / epilogue ===============================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;     // query row inside the block
+    const int st = threadIdx.x - 64;      // 0..127
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const long long q_row = q_row0 + row;
+
+    float m_used = -INFINITY;  // running (possibly stale) max, in scaled log2 units
+    float l_sum = 0.f;
+    // sparse class: Q~ = round(Q * qk_scale) and raw S is already in log2 units (c = 1)
+    // dense class : raw S, scaled inside the exponent (c = qk_scale), like FlashAttention
+    const float c = dense ? p.qk_scale : 1.0f;
+
+    if (n_tiles > 0) {
+      mbar_wait(&bars[Q_FULL], 0, p.err_flag);
+      if (!dense) {
+        // ref :87-88  q = (q * qk_scale).to(dtype) — elementwise, so swizzle-agnostic
+        uint4* q4 = reinterpret_cast<uint4*>(sQ);
+#pragma unroll 4
+        for (int i = 0; i < kTileBytes / 16 / 128; ++i) {
+          uint4 v = q4[st + i * 128];
+          uint32_t* e = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack2<kBF16>(e[t]);
+            e[t] = pack2<kBF16>(f.x * p.qk_scale, f.y * p.qk_scale);
+          }
+          q4[st + i * 128] = v;
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core proxy
+      }
+      mbar_arrive(&bars[Q_READY]);
+
+      BlockWalker it(s_mask, nwords);
+      int j = 0;
+      for (int blk = it.next(); blk >= 0; blk = it.next(), ++j) {
+        mbar_wait(&bars[S_FULL], j & 1, p.err_flag);
+        tc_fence_after();
+        float s[128];
+        {
+          uint32_t* su = reinterpret_cast<uint32_t*>(s);
+          tmem_ld32(tmem_S + lane_base + 0, su + 0);
+          tmem_ld32(tmem_S + lane_base + 32, su + 32);
+          tmem_ld32(tmem_S + lane_base + 64, su + 64);
+          tmem_ld32(tmem_S + lane_base + 96, su + 96);
+          tmem_ld_wait();
+        }
+        const long long col0 = static_cast<long long>(blk) * kBlock;
+        if (!dense && blk >= p.text_block_start && p.text_amp != 0.f) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) s[i] += p.text_amp;  // ref :113-114 (log2 units)
+        }
+        if (col0 + kBlock > kv_limit) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (col0 + i >= kv_limit) s[i] = -INFINITY;  // ref :117-118
+        }
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+        for (int i = 4; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, s[i]);
+          mx1 = fmaxf(mx1, s[i + 1]);
+          mx2 = fmaxf(mx2, s[i + 2]);
+          mx3 = fmaxf(mx3, s[i + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+        const float m_cand = fmaxf(m_used, mx);
+        // Lazy rescale: the reference rescales acc by exp2(m_old - m_new) every tile
+        // (:121-132).  O/l is invariant to the reference point, so we only move it when the
+        // max grew by more than 2^8 — the final O/l is the same up to fp32 rounding.
+        const bool need = (m_cand - m_used) > 8.0f;  // false for NaN (-inf - -inf)
+        if (__any_sync(0xffffffffu, need)) {
+          if (j > 0) {
+            const float alpha = (m_cand == -INFINITY) ? 1.0f : fast_exp2(m_used - m_cand);
+            // PV of tile j-1 has retired: S_FULL(j) is committed after the issuer waited on it
+#pragma unroll 1
+            for (int cc = 0; cc < 128; cc += 16) {
+              uint32_t o[16];
+              tmem_ld16(tmem_O + lane_base + cc, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tmem_O + lane_base + cc, o);
+            }
+            tmem_st_wait();
+            l_sum *= alpha;
+          }
+          m_used = m_cand;
+        }
+        const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(s[cc + 2 * i], c, -m_safe));
+            const float p1 = fast_exp2(fmaf(s[cc + 2 * i + 1], c, -m_safe));
+            sum0 += p0;  // ref :131 — l accumulates the unrounded fp32 p
+            sum1 += p1;
+            pk[i] = pack2<kBF16>(p0, p1);  // ref :128 — P is cast to the input dtype for PV
+          }
+          tmem_st16(tmem_S + lane_base + (cc >> 1), pk);
+        }
+        l_sum += sum0 + sum1;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[P_FULL]);
+      }
+      mbar_wait(&bars[PV_DONE], (n_tiles - 1) & 1, p.err_flag);
+      tc_fence_after();
+    }
+
+    // ---- epilogue: O / l -> global (ref :135-136); rows past the limit are zeros (:156) ----
+    const bool in_tensor = q_row < p.q_rows;
+    const bool zero_row = (n_tiles == 0) || (!dense && q_row >= p.q_limit_sparse);
+    const float inv_l = zero_row ? 0.f : 1.0f / l_sum;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + b * p.o_stride_b + q_row * p.o_stride_s +
+                     static_cast<long long>(h) * p.o_stride_h;
+#pragma unroll 1
+    for (int cc = 0; cc < 128; cc += 32) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        tmem_ld32(tmem_O + lane_base + cc, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0;
+      }
+      if (in_tensor) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          uint32_t* e = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float a = zero_row ? 0.f : __uint_as_float(o[i + 2 * t]) * inv_l;
+            const float bb = zero_row ? 0.f : __uint_as_float(o[i + 2 * t + 1]) * inv_l;
+            e[t] = pack2<kBF16>(a, bb);
+          }
+          *reinterpret_cast<uint4*>(orow + cc + i) = v;
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+static int make_tile_map(CUtensorMap* map, const void* base, int dtype, long long rows, int heads,
+                         int batch, long long stride_b, long long stride_s, long long stride_h) {
+  // dims (fastest first): d, row, head, batch.  Box {64, 128, 1, 1}, 128-B swizzle.
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(rows),
+                              static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(batch)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride_s) * 2,
+                                 static_cast<cuuint64_t>(stride_h) * 2,
+                                 static_cast<cuuint64_t>(stride_b) * 2};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(kBlock), 1, 1};
+  const cuuint32_t elem_strides[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt =
+      dtype == JENGA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  return encode_tensor_map(map, dt, 4, const_cast<void*>(base), dims, strides, box, elem_strides,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+static bool stride_ok(long long s) { return s > 0 && (s * 2) % 16 == 0; }
+
+int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
+  if (!a || !a->q || !a->k || !a->v || !a->out) return set_error(JENGA_E_INVALID, "null pointer");
+  if (a->dtype != JENGA_BF16 && a->dtype != JENGA_F16)
+    return set_error(JENGA_E_INVALID, "dtype must be bf16 or f16");
+  if (a->head_dim != kHeadDim)
+    return set_error(JENGA_E_UNSUPPORTED, "head_dim %d: only 128 is built", a->head_dim);
+  if (a->batch <= 0 || a->heads <= 0 || a->q_rows <= 0 || a->kv_rows <= 0)
+    return set_error(JENGA_E_INVALID, "empty shape");
+  if (a->nq_sparse < 0 || a->nq_dense < 0 || a->nq_sparse + a->nq_dense == 0)
+    return set_error(JENGA_E_INVALID, "no query blocks");
+  if (static_cast<long long>(a->nq_sparse + a->nq_dense - 1) * kBlock >= a->q_rows)
+    return set_error(JENGA_E_INVALID, "query blocks exceed q_rows");
+  const long long nb_kv = (a->kv_rows + kBlock - 1) / kBlock;
+  const int need_words = static_cast<int>((nb_kv + 31) / 32);
+  if (a->nq_sparse > 0 && (!a->mask_bits || a->mask_words < need_words))
+    return set_error(JENGA_E_INVALID, "mask_bits missing or mask_words %d < %d", a->mask_words,
+                     need_words);
+  const int words = a->nq_sparse > 0 ? a->mask_words : need_words;
+  if (words > kMaxMaskWords)
+    return set_error(JENGA_E_UNSUPPORTED, "more than %d key blocks", kMaxMaskWords * 32);
+  const long long strides[] = {a->q_stride_b, a->q_stride_s, a->q_stride_h, a->k_stride_b,
+                               a->k_stride_s, a->k_stride_h, a->v_stride_b, a->v_stride_s,
+                               a->v_stride_h, a->o_stride_b, a->o_stride_s, a->o_stride_h};
+  for (long long s : strides)
+    if (!stride_ok(s)) return set_error(JENGA_E_INVALID, "strides must be positive multiples of 8");
+  const uintptr_t ptrs[] = {(uintptr_t)a->q, (uintptr_t)a->k, (uintptr_t)a->v, (uintptr_t)a->out};
+  for (uintptr_t q : ptrs)
+    if (q % 16) return set_error(JENGA_E_INVALID, "pointers must be 16-byte aligned");
+  if (!(a->sm_scale > 0.f)) return set_error(JENGA_E_INVALID, "sm_scale must be positive");
+
+  CUtensorMap tm_q, tm_k, tm_v;
+  int rc;
+  if ((rc = make_tile_map(&tm_q, a->q, a->dtype, a->q_rows, a->heads, a->batch, a->q_stride_b,
+                          a->q_stride_s, a->q_stride_h)))
+    return rc;
+  if ((rc = make_tile_map(&tm_k, a->k, a->dtype, a->kv_rows, a->heads, a->batch, a->k_stride_b,
+                          a->k_stride_s, a->k_stride_h)))
+    return rc;
+  if ((rc = make_tile_map(&tm_v, a->v, a->dtype, a->kv_rows, a->heads, a->batch, a->v_stride_b,
+                          a->v_stride_s, a->v_stride_h)))
+    return rc;
+
+  KernelParams p{};
+  p.heads = a->heads;
+  p.nq_sparse = a->nq_sparse;
+  p.nq_dense = a->nq_dense;
+  p.nb_kv = static_cast<int>(nb_kv);
+  p.mask_words = words;
+  p.text_block_start = a->text_block_start;
+  p.q_rows = a->q_rows;
+  p.q_limit_sparse = a->q_limit_sparse;
+  p.kv_limit_sparse = a->kv_limit_sparse;
+  p.kv_limit_dense = a->kv_limit_dense;
+  p.qk_scale = static_cast<float>(static_cast<double>(a->sm_scale) * 1.44269504);  // ref :172
+  p.text_amp = a->text_amp;
+  p.mask_bits = a->mask_bits;
+  p.out = a->out;
+  p.o_stride_b = a->o_stride_b;
+  p.o_stride_s = a->o_stride_s;
+  p.o_stride_h = a->o_stride_h;
+  p.err_flag = a->err_flag;
+
+  const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
+  if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");
+  auto kern = a->dtype == JENGA_BF16 ? carved_attn_fwd_kernel<true> : carved_attn_fwd_kernel<false>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(carved_attn)");
+  kern<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_cuda_error(ce, "carved_attn launch");
+  return JENGA_OK;
+}
+
+}  // namespace jenga
