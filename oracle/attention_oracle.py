@@ -116,22 +116,32 @@ def build_block_onehot(
     block_neighbor_list: torch.Tensor | None = None,
     first_frame_blocks: int = 0,
     block: int = 128,
-) -> torch.Tensor:
+    tie_break: str = "low",
+    return_probs: bool = False,
+):
     """…triton_diffres.py:198-295 (HunyuanVideo) and wan/…:306-411 (adds first_frame_blocks)
     with the dtype flow the reference sees under torch.autocast(cuda, bfloat16)
     (SURVEY Appendix A-5): mean -> input dtype; bmm -> input dtype; * D^-1/2 -> input dtype;
-    softmax / sort / cumsum in fp32.  Ties are broken by lower index first (stable sort) — the
-    reference's torch.sort is unstable, so ties are outside the parity contract."""
+    softmax / sort / cumsum in fp32.
+    bf16 scores tie often.  The reference's torch.sort(descending=True) is not stable: on CUDA
+    (segmented radix sort) equal keys keep index order -> tie_break="low", which is what the
+    product kernel implements; on CPU the order of equal keys is arbitrary (tie_break="high"
+    is the other extreme), so fixtures are compared modulo swaps inside one tie group."""
     dt = query.dtype
     B, H, Nq, D = query.shape
     nq = (Nq + block - 1) // block
     qp = _round_like(query.float().reshape(B, H, -1, block, D).mean(dim=-2), dt)   # :216
     kp = _round_like(key.float().reshape(B, H, -1, block, D).mean(dim=-2), dt)     # :217
     scores = _round_like(qp @ kp.transpose(-1, -2), dt)                            # :227 bmm
-    scores = _round_like(scores * torch.tensor(D ** -0.5, dtype=torch.float32).to(dt).float(), dt)
+    # `bf16_tensor * python_float`: fp32 op-math with the scalar kept in fp32, one rounding
+    scores = _round_like(scores * torch.tensor(D ** -0.5, dtype=torch.float32), dt)
     normal = scores[..., :text_start_block]                                        # :235
     probs = torch.softmax(normal, dim=-1)                                          # :238 fp32
-    sorted_probs, indices = torch.sort(probs, dim=-1, descending=True, stable=True)  # :241
+    if tie_break == "low":
+        sorted_probs, indices = torch.sort(probs, dim=-1, descending=True, stable=True)  # :241
+    else:
+        sorted_probs, indices = torch.sort(probs.flip(-1), dim=-1, descending=True, stable=True)
+        indices = probs.shape[-1] - 1 - indices
     csum = torch.cumsum(sorted_probs, dim=-1)                                      # :242
     need = (csum <= prob_threshold).sum(dim=-1) + 1                                # :245-246
     need = torch.clamp(need, min=top_k)                                            # :247-250
@@ -149,7 +159,7 @@ def build_block_onehot(
         onehot[:, :, :first_frame_blocks, :first_frame_blocks] = True
     if text_blocks > 0:                                                            # :292-293
         onehot[..., text_start_block:min(text_start_block + text_blocks, num_blocks)] = True
-    return onehot
+    return (onehot, probs) if return_probs else onehot
 
 
 def block_sparse_attention(

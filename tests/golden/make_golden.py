@@ -1,0 +1,172 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz|json by executing the UNMODIFIED reference in the build container.
+
+Run here (CPU container, /root/reference mounted):   python tests/golden/make_golden.py
+The GPU box has no /root/reference; tests read only the committed fixtures.
+
+What is executed, and the two environment shims it needs (the reference files themselves are
+imported by path and not edited):
+
+* gilbert.py — imported with stub `matplotlib` modules (its plotting imports are absent here).
+* hyvideo|wan/modules/attention_block_triton_diffres.py
+    - `_triton_block_sparse_attn_fwd_kernel_onehot` runs under TRITON_INTERPRET=1 (numpy).  The
+      interpreter passes Python-float kernel arguments through as Python scalars, which would
+      make `q * qk_scale` a low-precision multiply; the COMPILED kernel receives them as fp32
+      scalars (triton mangles float -> fp32), so `_implicit_cvt` is wrapped to box floats as
+      fp32 tensors.  The interpreter's bfloat16 support is broken in triton 3.6 (garbage
+      output), so attention fixtures are fp16 — same kernel source, `dtype=tl.float16`.
+      `torch.cuda.device` is replaced by a null context (the launcher enters it on a CPU tensor).
+    - `_build_block_index_with_importance_optimized` runs on CPU tensors as is.  The pipelines
+      call it under torch.autocast("cuda", bfloat16) (pipeline_hunyuan_video_prores.py:663-665,
+      jenga_wan.py:135) whose fp32 op list promotes softmax and cumsum; CPU autocast does not,
+      so torch.softmax / torch.cumsum are wrapped to upcast to fp32 for the duration of the call.
+"""
+import contextlib
+import hashlib
+import importlib.util
+import io
+import json
+import os
+import sys
+import types
+from pathlib import Path
+
+os.environ["TRITON_INTERPRET"] = "1"
+
+import numpy as np
+import torch
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+sys.path.insert(0, str(OUT))
+
+
+def _import(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def sha16(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ----------------------------------------------------------------------------- gilbert
+def gilbert_goldens():
+    for m in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    ref = _import("ref_gilbert", REF / "gilbert.py")
+    cases = {}
+    full = {}
+    grids = [
+        # (name, t, h, w, sliced, keep_full_arrays)
+        ("toy_4x6x8", 4, 6, 8, 0, True),
+        ("toy_5x7x9", 5, 7, 9, 0, True),
+        ("toy_sliced_3x5x4", 3, 5, 4, 1, True),
+        ("toy_sliced_8x11x13", 8, 11, 13, 1, True),
+        ("odd_7x3x1", 7, 3, 1, 0, True),
+        ("hy_r0.5_32x22x40", 32, 22, 40, 0, False),
+        ("hy_r0.75_32x33x60", 32, 33, 60, 0, False),
+        ("hy720p_32x45x80", 32, 45, 80, 0, False),
+        ("wan1.3B_turbo_21x22x39", 21, 22, 39, 1, False),
+        ("wan1.3B_21x30x52", 21, 30, 52, 1, False),
+        ("wan14B_21x45x80", 21, 45, 80, 1, False),
+    ]
+    for name, t, h, w, sliced, keep in grids:
+        with contextlib.redirect_stdout(io.StringIO()):
+            if sliced:
+                l2h, h2l = ref.sliced_gilbert_mapping(t, h, w)
+                nbr = ref.sliced_gilbert_block_neighbor_mapping(t, h, w)
+            else:
+                l2h, h2l = ref.gilbert_mapping(t, h, w)
+                nbr = ref.gilbert_block_neighbor_mapping(t, h, w)
+        l2h = np.asarray(l2h, dtype=np.int64)
+        h2l = np.asarray(h2l, dtype=np.int64)
+        nbr = nbr.numpy().astype(np.bool_)
+        cases[name] = dict(t=t, h=h, w=w, sliced=sliced, l2h_sha=sha16(l2h), h2l_sha=sha16(h2l),
+                           nbr_sha=sha16(nbr), nbr_popcount=int(nbr.sum()),
+                           nbr_row_max=int(nbr.sum(1).max()), l2h_head=l2h[:8].tolist())
+        if keep:
+            full[name + "/l2h"] = l2h
+            full[name + "/h2l"] = h2l
+            full[name + "/nbr"] = nbr
+        print("gilbert", name, cases[name]["l2h_sha"], cases[name]["nbr_popcount"], flush=True)
+    (OUT / "gilbert.json").write_text(json.dumps(cases, indent=1))
+    np.savez_compressed(OUT / "gilbert_small.npz", **full)
+
+
+# ----------------------------------------------------------------------------- attention (a-9)
+def _patch_interpreter():
+    import triton.language as tl
+    import triton.runtime.interpreter as ti
+    orig = ti._implicit_cvt
+
+    def cvt(arg):
+        if isinstance(arg, float):  # compiled kernels see float args as fp32 scalars
+            return tl.tensor(ti.TensorHandle(np.array([arg], dtype=np.float32), tl.float32),
+                             tl.float32)
+        return orig(arg)
+
+    ti._implicit_cvt = cvt
+    torch.cuda.device = lambda d: contextlib.nullcontext()
+
+
+def attention_goldens():
+    _patch_interpreter()
+    import synth
+    hy = _import("ref_hy_attn", REF / "hyvideo/modules/attention_block_triton_diffres.py")
+    out = {}
+    for name, *_ in synth.ATTENTION_CASES:
+        c = synth.attention_case(name)
+        seqlens = torch.tensor([c["seqlen"]], dtype=torch.int32)
+        o = hy._triton_block_sparse_attention_onehot(
+            c["q"][:, :, :c["n_img"] * 128].contiguous(), c["k"], c["v"], seqlens, c["mask"],
+            128 ** -0.5, text_amp=c["amp"], text_block_start=c["n_img"])
+        out[name + "/o"] = o.numpy()
+        out[name + "/mask_sha"] = np.frombuffer(sha16(c["mask"].numpy()).encode(), dtype=np.uint8)
+        print("attention", name, float(o.float().abs().mean()), flush=True)
+    np.savez_compressed(OUT / "attention_fp16.npz", **out)
+
+
+# ----------------------------------------------------------------------------- mask builder (a-8)
+@contextlib.contextmanager
+def _cuda_autocast_dtype_flow():
+    sm, cs = torch.softmax, torch.cumsum
+    torch.softmax = lambda x, dim=-1, **kw: sm(x.float(), dim=dim, **kw)
+    torch.cumsum = lambda x, dim=-1, **kw: cs(x.float(), dim=dim, **kw)
+    try:
+        yield
+    finally:
+        torch.softmax, torch.cumsum = sm, cs
+
+
+def mask_goldens():
+    import synth
+    mods = {"hyvideo": _import("ref_hy_attn2", REF / "hyvideo/modules/attention_block_triton_diffres.py"),
+            "wan": _import("ref_wan_attn", REF / "wan/modules/attention_block_triton_diffres.py")}
+    out = {}
+    for name, *_ in synth.MASK_CASES:
+        c = synth.mask_case(name)
+        nb = c["n_img"] + c["n_txt"]
+        kw = dict(text_start_block=c["n_img"], num_blocks=nb, prob_threshold=c["p"],
+                  text_blocks=c["n_txt"], block_neighbor_list=c["nbr"])
+        if c["variant"] == "wan":
+            kw["first_frame_blocks"] = c["ff"]
+        with _cuda_autocast_dtype_flow():
+            m = mods[c["variant"]]._build_block_index_with_importance_optimized(
+                c["q"][:, :, :c["n_img"] * 128], c["k"], c["top_k"], 128, 128, **kw)
+        out[name + "/mask"] = m.numpy()
+        print("mask", name, "row counts", m[0, 0].sum(-1)[:8].tolist(), flush=True)
+    np.savez_compressed(OUT / "mask_builder.npz", **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gilbert", "attention", "mask"]
+    if "gilbert" in which:
+        gilbert_goldens()
+    if "attention" in which:
+        attention_goldens()
+    if "mask" in which:
+        mask_goldens()
