@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py — carved-attention hot path at the BASELINE.json workload.
+
+One "step" = one call of the AttenCarve operator (block pooling of q and k, block
+scoring/selection, block-sparse attention incl. the dense text rows) on one DiT layer's
+q,k,v at the HunyuanVideo 720x1280x125f shape: q,k,v [1, 115456, 24, 128] bf16
+(900 image blocks + 2 text blocks), Jenga-Base stage-0 settings (sa-drop 0.7 -> top_k 270,
+p_remain 0.3, text_amp 0, 26-neighbour adjacency of the 32x45x80 gilbert curve).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--drop 0.7]
+
+N>1 (torchrun): Ulysses — image tokens sharded over ranks outside the operator, all-to-all to
+(all tokens x H/N heads) inside (jenga_b200.ulysses), strong scaling of the same layer.
+
+value            carved-attention TFLOP/s, algorithmic FLOPs (4*128^3 per live tile from the
+                 popcount of the selection mask + dense text rows) / step time, inputs
+                 resident in HBM, CUDA-event timed, max over ranks.
+e2e              same FLOPs / time of the same call with q,k,v in PINNED HOST memory copied
+                 H2D inside the timed region and the result copied D2H.
+roofline         attention kernel alone (CUDA events on its stream), vs the measured bf16
+                 tensor peak in MEASURED_PEAKS.json.
+cpu_baseline     the oracle port (oracle/attention_oracle.py) on the host cores, bounded sample.
+--impl reference the reference's CPU-runnable path for this operator (torch SDPA with the
+                 expanded block mask, hyvideo/modules/attenion.py:102-107) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BLOCK = 128
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def workload(name: str, drop: float):
+    if name == "hy720p":
+        return dict(name="HunyuanVideo 720x1280x125f Jenga-Base layer (q,k,v [1,115456,24,128] bf16)",
+                    grid=(32, 45, 80), sliced=0, heads=24, text_tokens=256, text_valid=180,
+                    text_blocks=2, p_remain=0.3, drop=drop, variant="hyvideo", text_amp=0.0,
+                    first_frame=0, layers=60, computed_steps=23)
+    if name == "wan1.3b":
+        return dict(name="Wan2.1-1.3B 832x480x81f layer (q,k,v [1,32760,12,128])",
+                    grid=(21, 30, 52), sliced=1, heads=12, text_tokens=0, text_valid=0,
+                    text_blocks=0, p_remain=0.9, drop=0.5, variant="wan", text_amp=0.0,
+                    first_frame=(21 * 30 * 52 + 127) // 128 // 21, layers=30, computed_steps=60)
+    if name == "tiny":  # CI / smoke
+        return dict(name="tiny 8x16x16 grid, 4 heads", grid=(8, 16, 16), sliced=0, heads=4,
+                    text_tokens=256, text_valid=180, text_blocks=2, p_remain=0.3, drop=drop,
+                    variant="hyvideo", text_amp=0.0, first_frame=0, layers=1, computed_steps=1)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def synth_tokens(n_tokens, heads, dev, seed, gain=2.0, win=8):
+    """SURVEY §8d regime P: x = 0.5 N(0,1) + gain * c[block]; c = unit vectors low-pass
+    filtered along the curve order, then per-head RMS normalisation (weight 1) like the
+    reference's q/k norm.  Returns [1, n_tokens, heads, 128] bf16."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    nb = (n_tokens + BLOCK - 1) // BLOCK
+    c = torch.randn(heads, nb + win - 1, 128, generator=g, device=dev)
+    c = torch.nn.functional.avg_pool1d(c.transpose(1, 2), win, 1).transpose(1, 2)[:, :nb]
+    c = c / c.norm(dim=-1, keepdim=True)
+    out = torch.empty(1, n_tokens, heads, 128, dtype=torch.bfloat16, device=dev)
+    chunk = 64
+    for b0 in range(0, nb, chunk):
+        b1 = min(nb, b0 + chunk)
+        r0, r1 = b0 * BLOCK, min(n_tokens, b1 * BLOCK)
+        x = 0.5 * torch.randn(heads, (b1 - b0) * BLOCK, 128, generator=g, device=dev)
+        x = x + gain * c[:, b0:b1].repeat_interleave(BLOCK, dim=1)
+        x = x[:, : r1 - r0]
+        x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)
+        out[0, r0:r1] = x.transpose(0, 1).to(torch.bfloat16)
+    return out
+
+
+def build_inputs(wl, dev, heads=None, seed=1234):
+    from jenga_b200 import gilbert
+    t, h, w = wl["grid"]
+    heads = heads or wl["heads"]
+    n_img = t * h * w
+    S = n_img + wl["text_tokens"]
+    q = synth_tokens(S, heads, dev, seed)
+    k = synth_tokens(S, heads, dev, seed + 1)
+    v = torch.randn(1, S, heads, 128, generator=torch.Generator(device=dev).manual_seed(seed + 2),
+                    device=dev).to(torch.bfloat16)
+    nbr = gilbert.block_neighbor_mapping(t, h, w, sliced=bool(wl["sliced"]))
+    nb_img = (n_img + BLOCK - 1) // BLOCK
+    if wl["variant"] == "wan":
+        top_k = math.ceil(int(nb_img * (1 - wl["drop"])))       # wan/modules/model_mul.py:162-164
+        cu = None
+    else:
+        top_k = int((1 - wl["drop"]) * (n_img // BLOCK))          # models_mul…:242
+        cu = torch.tensor([0, n_img + wl["text_valid"], S], dtype=torch.int32, device=dev)
+    return dict(q=q, k=k, v=v, nbr=nbr, top_k=top_k, cu=cu, S=S, n_img=n_img, nb_img=nb_img,
+                heads=heads)
+
+
+def run_operator(wl, inp, q=None, k=None, v=None, return_bits=False):
+    from jenga_b200.attention import block_sparse_attention_variant
+    q = inp["q"] if q is None else q
+    k = inp["k"] if k is None else k
+    v = inp["v"] if v is None else v
+    return block_sparse_attention_variant(
+        wl["variant"], q, k, v, inp["top_k"], cu_seqlens_q=inp["cu"], cu_seqlens_kv=inp["cu"],
+        text_blocks=wl["text_blocks"], text_amp=wl["text_amp"], block_neighbor_list=inp["nbr"],
+        p_remain_rates=wl["p_remain"], first_frame_blocks=wl["first_frame"],
+        return_mask_bits=return_bits)
+
+
+def algorithmic_flops(wl, inp, bits):
+    """4*128*128*128 per live (q-block, k-block) tile + dense text rows (BASELINE.md FLOP rule)."""
+    words = bits.to(torch.int64) & 0xFFFFFFFF
+    pop = 0
+    x = words
+    # popcount via byte table-free bit tricks
+    x = x - ((x >> 1) & 0x5555555555555555)
+    x = (x & 0x3333333333333333) + ((x >> 2) & 0x3333333333333333)
+    x = (x + (x >> 4)) & 0x0F0F0F0F0F0F0F0F
+    pop = int(((x * 0x0101010101010101) >> 56 & 0xFF).sum().item())
+    tile = 4 * BLOCK * BLOCK * 128
+    text_rows = wl["text_blocks"] * BLOCK
+    nb_all = (inp["S"] + BLOCK - 1) // BLOCK
+    dense = 4 * inp["heads"] * text_rows * nb_all * BLOCK * 128
+    return pop * tile + dense, pop
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.samples.append([s.strip() for s in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, val in zip(names, s[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()), default=None),
+                "samples": len(self.samples), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16_burst=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port / reference SDPA path) — bounded samples
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(wl, kind: str, budget_s: float = 12.0):
+    """Times a bounded sample of the SAME operator math on the host cores: one head, a few query
+    blocks at the workload's key length and density.  kind="port": oracle tile loop;
+    kind="sdpa": torch SDPA with the expanded block mask (the reference's CPU-runnable path)."""
+    from oracle import attention_oracle as orc
+    ncores = os.cpu_count() or 1
+    # the tile loop of the port is many small GEMMs: past ~32 threads it only adds sync cost
+    torch.set_num_threads(ncores if kind == "sdpa" else min(32, ncores))
+    t, h, w = wl["grid"]
+    n_img = t * h * w
+    S = n_img + wl["text_tokens"]
+    nb = (S + BLOCK - 1) // BLOCK
+    nb_img = (n_img + BLOCK - 1) // BLOCK
+    nq = 4 if kind == "sdpa" else 1
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(1, 1, nq * BLOCK, 128, generator=g).bfloat16()
+    k = torch.randn(1, 1, nb * BLOCK, 128, generator=g).bfloat16()
+    v = torch.randn(1, 1, nb * BLOCK, 128, generator=g).bfloat16()
+    live = max(1, int(round((1 - wl["drop"]) * nb_img))) + wl["text_blocks"]
+    mask = torch.zeros(1, 1, nq, nb, dtype=torch.bool)
+    for i in range(nq):
+        idx = torch.randperm(nb_img, generator=g)[: live - wl["text_blocks"]]
+        mask[0, 0, i, idx] = True
+        mask[0, 0, i, nb_img:] = True
+    flops = 4 * BLOCK * BLOCK * 128 * int(mask.sum())
+    reps, t_total = 0, 0.0
+    while t_total < budget_s and reps < 50:
+        t0 = time.perf_counter()
+        if kind == "port":
+            orc.carved_attention_rows(q, k, v, mask, S, 128 ** -0.5, 0.0, nb_img)
+        else:
+            big = mask.repeat_interleave(BLOCK, 2).repeat_interleave(BLOCK, 3)
+            torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=big)
+        t_total += time.perf_counter() - t0
+        reps += 1
+    tf = flops * reps / t_total / 1e12
+    sample = (f"1 head x {nq} query blocks x {live} live key blocks of {nb} (S={S}), "
+              f"{reps} reps, {t_total:.1f}s")
+    return tf, sample, t_total / reps, torch.get_num_threads()
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hy720p")
+    ap.add_argument("--drop", type=float, default=0.7)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = workload(args.workload, args.drop)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    metric = "carved_attn_tflops"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        ncores = os.cpu_count()
+        for _ in range(max(1, args.warmup)):
+            cpu_sample(wl, "sdpa", budget_s=0.0)
+        for _ in range(max(1, args.steps)):
+            tf_i, sample, sec, ncores = cpu_sample(wl, "sdpa", budget_s=0.0)
+            vals.append((tf_i, sec))
+        tf = sum(v[0] for v in vals) / len(vals)
+        ms = 1e3 * sum(v[1] for v in vals) / len(vals)
+        line = {"impl": "reference", "metric": metric, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": wl["name"], "sa_drop": wl["drop"], "p_remain": wl["p_remain"]},
+                "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
+                                 "sample": "torch SDPA + expanded block mask (reference CPU path, "
+                                           "hyvideo/modules/attenion.py:102-107): " + sample},
+                "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (jenga_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    if world > 1:
+        from jenga_b200 import ulysses
+        state = ulysses.bench_setup(wl, build_inputs, dev, rank, world)
+        step = lambda: ulysses.bench_step(wl, state)  # noqa: E731
+        inp = state["inp"]
+    else:
+        inp = build_inputs(wl, dev)
+        step = lambda: run_operator(wl, inp)  # noqa: E731
+
+    # FLOPs from the selection mask of this exact input (reported with the number)
+    if world > 1:
+        flops, pop = ulysses.bench_flops(wl, state, algorithmic_flops)
+    else:
+        _, bits = run_operator(wl, inp, return_bits=True)
+        flops, pop = algorithmic_flops(wl, inp, bits)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    clocks = clk.summary()
+
+    # ---- roofline: the attention kernel alone, CUDA events on its stream (N=1 path shape)
+    roof = None
+    pk = peaks()
+    if world == 1:
+        from jenga_b200 import attention as A
+        _, bits = run_operator(wl, inp, return_bits=True)
+        S, nb_img = inp["S"], inp["nb_img"]
+        out = torch.empty_like(inp["q"])
+        seq = inp["cu"][1:2].contiguous() if inp["cu"] is not None else None
+        def attn_only():
+            A._launch(inp["q"], inp["k"], inp["v"], bits, nb_img, wl["text_blocks"], 128 ** -0.5, wl["text_amp"],
+                      nb_img, S, S, ((S + 127) // 128) * 128, out, seq, torch.bfloat16)
+        for _ in range(3):
+            attn_only()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_it = max(5, args.steps)
+        a0.record()
+        for _ in range(n_it):
+            attn_only()
+        a1.record()
+        torch.cuda.synchronize()
+        ams = a0.elapsed_time(a1) / n_it
+        ach = flops / (ams * 1e-3) / 1e12
+        traffic = None
+        tp = ROOT / "profiles" / "attn_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "kernel": "carved_attn_fwd_kernel", "achieved": ach, "peak": pk["bf16_burst"],
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"], "traffic": traffic, "ms_per_launch": ams,
+                "peak_source": pk["source"] + ", bf16 burst (kernel timed alone)",
+                "algorithmic_flops_per_launch": flops, "live_tiles": pop}
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e and world == 1:
+        hq, hk, hv = (x.cpu().pin_memory() for x in (inp["q"], inp["k"], inp["v"]))
+        dq, dk, dv = (torch.empty_like(x) for x in (inp["q"], inp["k"], inp["v"]))
+        hout = torch.empty((1, inp["S"], inp["heads"] * 128), dtype=torch.bfloat16).pin_memory()
+        def e2e_step():
+            dq.copy_(hq, non_blocking=True)
+            dk.copy_(hk, non_blocking=True)
+            dv.copy_(hv, non_blocking=True)
+            o = run_operator(wl, inp, dq, dk, dv)
+            hout.copy_(o, non_blocking=True)
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        n_it = max(3, min(args.steps, 5))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n_it):
+            e2e_step()
+        b1.record()
+        torch.cuda.synchronize()
+        ems = b0.elapsed_time(b1) / n_it
+        e2e = {"value": flops / (ems * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ems,
+               "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in (hq, hk, hv)),
+               "d2h_bytes_per_step": hout.numel() * hout.element_size()}
+        del hq, hk, hv, dq, dk, dv, hout
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tf, sample, _, ncores = cpu_sample(wl, "port")
+        cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
+               "sample": "oracle/attention_oracle.carved_attention_rows: " + sample}
+
+    if rank == 0:
+        value = flops / (ms * 1e-3) / 1e12
+        launches = 4 if world == 1 else 4  # block_pool x2, select_blocks, carved_attn per step
+        line = {
+            "metric": metric, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "sa_drop": wl["drop"], "top_k": inp["top_k"],
+                       "p_remain": wl["p_remain"], "text_blocks": wl["text_blocks"],
+                       "live_tiles": pop, "algorithmic_tflop_per_step": flops / 1e12,
+                       "l2": "inputs (2.8 GB) larger than L2, no flush",
+                       "parallelism": "1 gpu" if world == 1 else f"ulysses{world}",
+                       "hot_path_sec_per_video": ms * 1e-3 * wl["layers"] * wl["computed_steps"]},
+            "clocks": clocks, "gpu_launches": launches * args.steps,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

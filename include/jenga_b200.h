@@ -105,6 +105,10 @@ typedef struct JengaAttnArgs {
   /* dense class (ref flash_attn_func on the text rows): plain softmax(q k^T sm_scale) v over
    * key columns < kv_limit_dense. */
   int64_t kv_limit_dense;
+  /* optional device int32: when non-NULL, *seqlen_dev replaces kv_limit_sparse and
+   * q_limit_sparse at run time (ref :58 reads cu_seqlens_q[1] on the device, :328-329). */
+  const int32_t* seqlen_dev;
+  int32_t out_dtype; /* == dtype, or JENGA_F32 (wan variant returns the query dtype, :530-532) */
   int32_t* err_flag; /* device int, may be NULL: set non-zero by in-kernel watchdogs */
 } JengaAttnArgs;
 
@@ -115,6 +119,91 @@ int jenga_carved_attn_fwd(const JengaAttnArgs* args, void* stream);
  * -> packed bit rows [BH, nq, mask_words]. */
 int jenga_mask_onehot_to_bits(const uint8_t* onehot, uint32_t* bits, int64_t rows, int32_t nb,
                               int32_t mask_words, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-8) block scoring and selection.
+ * ref: hyvideo/modules/attention_block_triton_diffres.py:198-295
+ *      (_build_block_index_with_importance_optimized); wan twin :306-411 adds
+ *      first_frame_blocks (:400-406).
+ *
+ * Step 1 — jenga_block_pool: pooled[b,h,blk,:] = mean of the block's 128 rows (ref :216-217),
+ *   rounded to `out_dtype`.  x is [B,S,H,D] (element strides), rows >= S count as zeros
+ *   (the Wan/I2V variants zero-pad first).  in_dtype JENGA_F32 means "Wan q/k": every element
+ *   is rounded to bf16 before pooling (wan/...:456-463) and, if cast_out != NULL, the bf16
+ *   copy is written contiguously as [B,S,H,D].
+ * Step 2 — jenga_select_blocks: scores = round(round(qp kp^T) D^-1/2) over the first n_img
+ *   key blocks (:227,:235), fp32 softmax (:238), descending sort with ties in index order,
+ *   n = max(#(cumsum <= p)+1, top_k) (:241-250), first n blocks, OR neighbour rows
+ *   (:280-289), OR first-frame square (wan), OR text columns (:292-293).  Output: packed bit
+ *   rows [BH, nq, mask_words] for jenga_carved_attn_fwd; out_counts (optional) gets n.
+ *   nbr_bits are packed rows of the bool [nbr_rows, >= n_img] adjacency matrix
+ *   (use jenga_mask_onehot_to_bits once per curve).
+ * ---------------------------------------------------------------------------------------- */
+int jenga_block_pool(const void* x, void* pooled, void* cast_out, int32_t in_dtype,
+                     int32_t out_dtype, int32_t batch, int32_t heads, int32_t head_dim,
+                     int64_t rows, int64_t stride_b, int64_t stride_s, int64_t stride_h,
+                     int32_t n_blocks, void* stream);
+
+typedef struct JengaSelectArgs {
+  const void* q_pool; /* [BH, nq, D]       */
+  const void* k_pool; /* [BH, nk_pool, D]  */
+  int32_t dtype;      /* JENGA_BF16 | JENGA_F16 */
+  int32_t batch_heads, head_dim;
+  int32_t nq;      /* image query blocks                         */
+  int32_t nk_pool; /* rows per head in k_pool (>= n_img)         */
+  int32_t n_img;   /* ranked key blocks == text_start_block      */
+  int32_t nb;      /* all key blocks                             */
+  int32_t mask_words;
+  int32_t top_k;
+  float p_threshold; /* ref prob_threshold / p_remain_rates      */
+  int32_t text_blocks;
+  int32_t first_frame_blocks;
+  const uint32_t* nbr_bits;
+  int32_t nbr_rows, nbr_words;
+  uint32_t* out_bits;
+  int32_t* out_counts;
+} JengaSelectArgs;
+
+int jenga_select_blocks(const JengaSelectArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-5, a-6, part of a-8) HunyuanVideo attention prologue: per-head RMSNorm(q,k), RoPE(q,k)
+ * on the image tokens, img||txt concatenation and block mean-pooling in one pass.
+ * ref: hyvideo/modules/models_mul_block_gc_ha_multigpu.py:200-241 (double stream),
+ *      :417-435 (single stream); norm_layers.py:32-59; posemb_layers.py:133-137,181-229;
+ *      pooling attention_block_triton_diffres.py:216-217.
+ * img_qkv / txt_qkv are the fused QKV projections viewed as [B, tokens, 3, H, D] with element
+ * strides (batch, token, which-of-qkv, head); D == 128 contiguous.  Norm weights are [D] in
+ * `dtype` (all NULL == elementwise_affine=False).  rope_cos/rope_sin are fp32 [rows, D]
+ * tables (interleaved-pair layout of get_nd_rotary_pos_embed); rope_index (optional, int64
+ * [img_tokens]) gathers table rows per token (freqs_cos[hilbert_order], jenga_hyvideo.py:117).
+ * Outputs q,k,v are contiguous [B, S, H, D], S = img_tokens + txt_tokens; q_pool / k_pool
+ * (optional, together) are [B, H, ceil(S/128), D].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct JengaHyPrologueArgs {
+  const void* img_qkv;
+  const void* txt_qkv; /* may be NULL when txt_tokens == 0 */
+  int32_t dtype;
+  int32_t batch, heads, head_dim;
+  int64_t img_tokens, txt_tokens;
+  int64_t img_stride_b, img_stride_s, img_stride_w, img_stride_h;
+  int64_t txt_stride_b, txt_stride_s, txt_stride_w, txt_stride_h;
+  const void* w_img_q;
+  const void* w_img_k;
+  const void* w_txt_q;
+  const void* w_txt_k;
+  float eps;
+  const float* rope_cos;
+  const float* rope_sin;
+  const int64_t* rope_index;
+  void* q;
+  void* k;
+  void* v;
+  void* q_pool;
+  void* k_pool;
+} JengaHyPrologueArgs;
+
+int jenga_hy_prologue(const JengaHyPrologueArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,37 @@ class JengaAttnArgs(C.Structure):
         ("sm_scale", C.c_float), ("text_amp", C.c_float), ("text_block_start", C.c_int32),
         ("kv_limit_sparse", C.c_int64), ("q_limit_sparse", C.c_int64),
         ("kv_limit_dense", C.c_int64),
+        ("seqlen_dev", C.c_void_p), ("out_dtype", C.c_int32),
         ("err_flag", C.c_void_p),
+    ]
+
+
+class JengaSelectArgs(C.Structure):
+    _fields_ = [
+        ("q_pool", C.c_void_p), ("k_pool", C.c_void_p), ("dtype", C.c_int32),
+        ("batch_heads", C.c_int32), ("head_dim", C.c_int32), ("nq", C.c_int32),
+        ("nk_pool", C.c_int32), ("n_img", C.c_int32), ("nb", C.c_int32),
+        ("mask_words", C.c_int32), ("top_k", C.c_int32), ("p_threshold", C.c_float),
+        ("text_blocks", C.c_int32), ("first_frame_blocks", C.c_int32),
+        ("nbr_bits", C.c_void_p), ("nbr_rows", C.c_int32), ("nbr_words", C.c_int32),
+        ("out_bits", C.c_void_p), ("out_counts", C.c_void_p),
+    ]
+
+
+class JengaHyPrologueArgs(C.Structure):
+    _fields_ = [
+        ("img_qkv", C.c_void_p), ("txt_qkv", C.c_void_p), ("dtype", C.c_int32),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("img_tokens", C.c_int64), ("txt_tokens", C.c_int64),
+        ("img_stride_b", C.c_int64), ("img_stride_s", C.c_int64), ("img_stride_w", C.c_int64),
+        ("img_stride_h", C.c_int64),
+        ("txt_stride_b", C.c_int64), ("txt_stride_s", C.c_int64), ("txt_stride_w", C.c_int64),
+        ("txt_stride_h", C.c_int64),
+        ("w_img_q", C.c_void_p), ("w_img_k", C.c_void_p), ("w_txt_q", C.c_void_p),
+        ("w_txt_k", C.c_void_p), ("eps", C.c_float),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_index", C.c_void_p),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("q_pool", C.c_void_p), ("k_pool", C.c_void_p),
     ]
 
 
@@ -58,6 +88,14 @@ def _load() -> C.CDLL:
     lib.jenga_gilbert_block_neighbors_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int,
                                                        C.c_int, C.c_void_p]
     lib.jenga_gilbert_block_neighbors_host.restype = C.c_int
+    lib.jenga_block_pool.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                     C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.jenga_block_pool.restype = C.c_int
+    lib.jenga_select_blocks.argtypes = [C.POINTER(JengaSelectArgs), C.c_void_p]
+    lib.jenga_select_blocks.restype = C.c_int
+    lib.jenga_hy_prologue.argtypes = [C.POINTER(JengaHyPrologueArgs), C.c_void_p]
+    lib.jenga_hy_prologue.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 1:

@@ -105,7 +105,207 @@ def carved_attention_fwd(
     a.kv_limit_sparse = Sk if kv_limit_sparse is None else kv_limit_sparse
     a.q_limit_sparse = Sq if q_limit_sparse is None else q_limit_sparse
     a.kv_limit_dense = Sk if kv_limit_dense is None else kv_limit_dense
+    a.seqlen_dev = None
+    a.out_dtype = _lib.JENGA_F32 if out.dtype == torch.float32 else a.dtype
     a.err_flag = err_flag.data_ptr() if err_flag is not None else None
     with torch.cuda.device(q.device):
         check(lib.jenga_carved_attn_fwd(C.byref(a), _stream_ptr(q.device)), "carved_attn_fwd")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# block pooling + selection (a-8)
+# --------------------------------------------------------------------------------------------
+def block_pool(x: torch.Tensor, n_blocks: int, cast_out: torch.Tensor | None = None) -> torch.Tensor:
+    """Mean over each 128-row block of x [B,S,H,D] -> pooled [B,H,n_blocks,D]
+    (ref …triton_diffres.py:216-217).  fp32 input is rounded to bf16 first (wan/…:456-463);
+    `cast_out` [B,S,H,D] bf16 then receives the rounded copy."""
+    _require_cuda(x)
+    B, S, H, D = x.shape
+    if x.stride(3) != 1:
+        raise ValueError("head_dim must be contiguous")
+    in_code = _lib.JENGA_F32 if x.dtype == torch.float32 else _dtype_code(x)
+    out_dtype = torch.bfloat16 if x.dtype == torch.float32 else x.dtype
+    pooled = torch.empty((B, H, n_blocks, D), dtype=out_dtype, device=x.device)
+    if cast_out is not None:
+        if cast_out.shape != x.shape or cast_out.dtype != torch.bfloat16 or not cast_out.is_contiguous():
+            raise ValueError("cast_out must be a contiguous bf16 tensor shaped like x")
+    with torch.cuda.device(x.device):
+        check(lib.jenga_block_pool(x.data_ptr(), pooled.data_ptr(),
+                                   cast_out.data_ptr() if cast_out is not None else None,
+                                   in_code, _dtype_code(pooled), B, H, D, S, x.stride(0), x.stride(1),
+                                   x.stride(2), n_blocks, _stream_ptr(x.device)), "block_pool")
+    return pooled
+
+
+_NBR_CACHE: dict = {}
+
+
+def neighbour_bits(block_neighbor_list: torch.Tensor, device) -> torch.Tensor:
+    """Packs (and caches per tensor/device) the bool adjacency matrix the reference passes as
+    `block_neighbor_list` (gilbert.py:597/:679 output) into bit rows on `device`."""
+    key = (block_neighbor_list.data_ptr(), tuple(block_neighbor_list.shape),
+           block_neighbor_list._version, str(device))
+    hit = _NBR_CACHE.get(key)
+    if hit is not None:
+        return hit
+    m = block_neighbor_list.to(device=device, dtype=torch.bool)
+    bits = mask_onehot_to_bits(m)
+    if len(_NBR_CACHE) > 64:
+        _NBR_CACHE.clear()
+    _NBR_CACHE[key] = bits
+    return bits
+
+
+def select_blocks(q_pool: torch.Tensor, k_pool: torch.Tensor, *, n_img: int, nb: int, top_k: int,
+                  p_threshold: float, text_blocks: int, first_frame_blocks: int = 0,
+                  nbr_bits: torch.Tensor | None = None, return_counts: bool = False):
+    """Pooled scores -> per-(head, query block) bit rows of attended key blocks
+    (ref …triton_diffres.py:227-293; wan first-frame rule :400-406)."""
+    _require_cuda(q_pool, k_pool)
+    B, H, nq, D = q_pool.shape
+    if not q_pool.is_contiguous() or not k_pool.is_contiguous():
+        raise ValueError("pooled tensors must be contiguous")
+    words = (nb + 31) // 32
+    bits = torch.empty((B, H, nq, words), dtype=torch.int32, device=q_pool.device)
+    counts = torch.empty((B, H, nq), dtype=torch.int32, device=q_pool.device) if return_counts else None
+    a = _lib.JengaSelectArgs()
+    a.q_pool, a.k_pool, a.dtype = q_pool.data_ptr(), k_pool.data_ptr(), _dtype_code(q_pool)
+    a.batch_heads, a.head_dim, a.nq = B * H, D, nq
+    a.nk_pool, a.n_img, a.nb, a.mask_words = k_pool.shape[2], n_img, nb, words
+    a.top_k, a.p_threshold = int(top_k), float(p_threshold)
+    a.text_blocks, a.first_frame_blocks = int(text_blocks), int(first_frame_blocks)
+    if nbr_bits is not None:
+        a.nbr_bits, a.nbr_rows, a.nbr_words = nbr_bits.data_ptr(), nbr_bits.shape[0], nbr_bits.shape[1]
+    else:
+        a.nbr_bits, a.nbr_rows, a.nbr_words = None, 0, 0
+    a.out_bits = bits.data_ptr()
+    a.out_counts = counts.data_ptr() if counts is not None else None
+    with torch.cuda.device(q_pool.device):
+        check(lib.jenga_select_blocks(C.byref(a), _stream_ptr(q_pool.device)), "select_blocks")
+    return (bits, counts) if return_counts else bits
+
+
+def bits_to_onehot(bits: torch.Tensor, nb: int) -> torch.Tensor:
+    """Test/debug helper: expands packed bit rows back to the reference's bool one-hot."""
+    shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+    oh = ((bits.unsqueeze(-1) >> shifts) & 1).bool().flatten(-2)
+    return oh[..., :nb]
+
+
+# --------------------------------------------------------------------------------------------
+# the operator (a-11)
+# --------------------------------------------------------------------------------------------
+_VARIANT_DEFAULTS = {
+    # variant: (text_blocks, p_remain_rates)   ref: hyvideo/…:399-424, hyvideo_i2v/…:398-423, wan/…:535-562
+    "hyvideo": (2, 0.5),
+    "hyvideo_i2v": (4, 0.5),
+    "wan": (0, 0.9),
+}
+
+
+def block_sparse_attention_variant(
+    variant: str, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, top_k: int,
+    block_size_M: int = 128, block_size_N: int = 128, cu_seqlens_q=None, cu_seqlens_kv=None,
+    max_seqlen_q=None, max_seqlen_kv=None, text_blocks=None, text_amp: float = 0.0,
+    block_neighbor_list=None, shape_xfuse: bool = False, p_remain_rates=None,
+    first_frame_blocks: int = 0, return_mask_bits: bool = False,
+):
+    """AttenCarve operator, [B,S,H,D] in -> [B,S,H*D] (or [B,S,H,D] when shape_xfuse).
+    Same arguments, defaults and quirks as the reference function of the same name; see the
+    variant table above for the file each one mirrors.  Three launches on the current stream
+    (2x block_pool, select_blocks) + one carved-attention launch; no host synchronisation."""
+    if variant not in _VARIANT_DEFAULTS:
+        raise ValueError(f"unknown variant {variant!r}")
+    d_text, d_p = _VARIANT_DEFAULTS[variant]
+    text_blocks = d_text if text_blocks is None else int(text_blocks)
+    p_remain_rates = d_p if p_remain_rates is None else float(p_remain_rates)
+    if block_size_M != BLOCK or block_size_N != BLOCK:
+        raise ValueError("only 128x128 blocks are built (the only size the reference launches)")
+    _require_cuda(query, key, value)
+    B, S, H, D = query.shape
+    assert D in (16, 32, 64, 128), "ref :155 — head_dim must be one of {16,32,64,128}"
+    out_dtype = query.dtype
+    use_cu = variant != "wan" and cu_seqlens_q is not None and cu_seqlens_kv is not None
+    seqlen_dev = None
+    if use_cu:
+        # ref :328-329 — only element [1] is read, on the device
+        seqlen_dev = cu_seqlens_q[1:2].to(device=query.device, dtype=torch.int32)
+    if variant == "hyvideo" and S % BLOCK != 0:
+        # ref :216 reshape fails on ragged S (the padded copies of :331-335 are never used)
+        raise ValueError(f"hyvideo variant needs S % 128 == 0, got {S}")
+    nb = (S + BLOCK - 1) // BLOCK
+    normal_blocks = nb - text_blocks
+    if normal_blocks < 0:
+        raise ValueError("more text blocks than blocks")
+    # ---- dtype handling: wan casts everything to bf16 first (:456-463)
+    q, k, v = query, key, value
+    q_pool = k_pool = None
+    if variant == "wan":
+        def to_bf16_with_pool(x, want_pool, n_pool):
+            if x.dtype == torch.bfloat16:
+                return x, (block_pool(x, n_pool) if want_pool and n_pool > 0 else None)
+            xf = x if x.dtype == torch.float32 else x.float()
+            xc = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            pooled = block_pool(xf, max(n_pool, 1), cast_out=xc)
+            return xc, (pooled if want_pool and n_pool > 0 else None)
+        q, q_pool = to_bf16_with_pool(q, True, normal_blocks)
+        k, k_pool = to_bf16_with_pool(k, True, normal_blocks)
+        v, _ = to_bf16_with_pool(v, False, 0) if v.dtype != torch.bfloat16 else (v, None)
+    elif not (q.dtype == k.dtype == v.dtype):
+        raise ValueError("q, k, v must share a dtype")
+    mask_bits = None
+    if normal_blocks > 0:
+        if q_pool is None:
+            q_pool = block_pool(q, normal_blocks)
+        if k_pool is None:
+            k_pool = block_pool(k, normal_blocks)
+        nbr = neighbour_bits(block_neighbor_list, q.device) if block_neighbor_list is not None else None
+        mask_bits = select_blocks(q_pool, k_pool, n_img=normal_blocks, nb=nb, top_k=top_k,
+                                  p_threshold=p_remain_rates, text_blocks=text_blocks,
+                                  first_frame_blocks=first_frame_blocks if variant == "wan" else 0,
+                                  nbr_bits=nbr)
+    out = torch.empty((B, S, H, D), dtype=out_dtype if variant == "wan" else q.dtype, device=q.device)
+    a_out_dtype = out.dtype
+    limit = S  # no cu_seqlens: seqlens = [context_size] (:336 / wan :452)
+    o = _launch(q, k, v, mask_bits, normal_blocks, text_blocks, D ** -0.5, text_amp, normal_blocks,
+                limit, limit, nb * BLOCK, out, seqlen_dev, a_out_dtype)
+    if not shape_xfuse:
+        o = o.reshape(B, S, H * D)
+    return (o, mask_bits) if return_mask_bits else o
+
+
+def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_block_start,
+            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype):
+    B, Sq, H, D = q.shape
+    a = JengaAttnArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.dtype = _dtype_code(q)
+    a.out_dtype = _lib.JENGA_F32 if out_dtype == torch.float32 else a.dtype
+    a.batch, a.heads, a.head_dim = B, H, D
+    a.q_rows, a.kv_rows = Sq, k.shape[1]
+    a.q_stride_b, a.q_stride_s, a.q_stride_h = q.stride(0), q.stride(1), q.stride(2)
+    a.k_stride_b, a.k_stride_s, a.k_stride_h = k.stride(0), k.stride(1), k.stride(2)
+    a.v_stride_b, a.v_stride_s, a.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
+    a.o_stride_b, a.o_stride_s, a.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
+    a.nq_sparse, a.nq_dense = nq_sparse, nq_dense
+    a.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
+    a.mask_words = mask_bits.shape[-1] if mask_bits is not None else 0
+    a.sm_scale, a.text_amp, a.text_block_start = sm_scale, float(text_amp), text_block_start
+    a.kv_limit_sparse, a.q_limit_sparse, a.kv_limit_dense = kv_limit_sparse, q_limit_sparse, kv_limit_dense
+    a.seqlen_dev = seqlen_dev.data_ptr() if seqlen_dev is not None else None
+    a.err_flag = None
+    with torch.cuda.device(q.device):
+        check(lib.jenga_carved_attn_fwd(C.byref(a), _stream_ptr(q.device)), "carved_attn_fwd")
+    return out
+
+
+def block_sparse_attention(query, key, value, top_k, block_size_M=128, block_size_N=128,
+                           cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None,
+                           max_seqlen_kv=None, text_blocks=2, text_amp=0.0,
+                           block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5):
+    """Drop-in for hyvideo/modules/attention_block_triton_diffres.py:399 block_sparse_attention."""
+    return block_sparse_attention_variant(
+        "hyvideo", query, key, value, top_k, block_size_M, block_size_N, cu_seqlens_q,
+        cu_seqlens_kv, max_seqlen_q, max_seqlen_kv, text_blocks, text_amp, block_neighbor_list,
+        shape_xfuse, p_remain_rates)

@@ -26,7 +26,6 @@ CXX_SOURCES = ["gilbert.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "--use_fast_math",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",

@@ -140,3 +140,19 @@ extern "C" int jenga_mask_onehot_to_bits(const uint8_t* onehot, uint32_t* bits, 
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "onehot_to_bits launch");
 }
+
+extern "C" int jenga_block_pool(const void* x, void* pooled, void* cast_out, int32_t in_dtype,
+                                int32_t out_dtype, int32_t batch, int32_t heads, int32_t head_dim,
+                                int64_t rows, int64_t stride_b, int64_t stride_s, int64_t stride_h,
+                                int32_t n_blocks, void* stream) {
+  return block_pool_impl(x, pooled, cast_out, in_dtype, out_dtype, batch, heads, head_dim, rows,
+                         stride_b, stride_s, stride_h, n_blocks, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int jenga_select_blocks(const JengaSelectArgs* args, void* stream) {
+  return select_blocks_impl(args, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int jenga_hy_prologue(const JengaHyPrologueArgs* args, void* stream) {
+  return hy_prologue_impl(args, static_cast<cudaStream_t>(stream));
+}

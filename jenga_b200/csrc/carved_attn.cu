@@ -56,8 +56,10 @@ struct KernelParams {
   float qk_scale;             // sm_scale * log2(e)
   float text_amp;
   const uint32_t* mask_bits;
+  const int* seqlen_dev;      // optional: overrides q_limit_sparse / kv_limit_sparse
   void* out;
   long long o_stride_b, o_stride_s, o_stride_h;  // elements
+  int out_f32;                // 1: write fp32 (values still rounded through the MMA dtype)
   int* err_flag;
 };
 
@@ -106,9 +108,13 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
   const int b = bh / p.heads;
   const int h = bh - b * p.heads;
   const long long q_row0 = static_cast<long long>(qb) * kBlock;
-  const long long kv_limit = dense ? p.kv_limit_dense : p.kv_limit_sparse;
+  // ref :58 — seqlen is read from device memory (cu_seqlens_q[1]); no host round trip
+  const long long seqlen_over = p.seqlen_dev ? static_cast<long long>(__ldg(p.seqlen_dev)) : -1;
+  const long long q_limit_sparse = seqlen_over >= 0 ? seqlen_over : p.q_limit_sparse;
+  const long long kv_limit =
+      dense ? p.kv_limit_dense : (seqlen_over >= 0 ? seqlen_over : p.kv_limit_sparse);
   // ref :59-61 — a sparse q block entirely past seqlen is skipped (its rows stay zero)
-  const bool skip_all = (!dense && q_row0 >= p.q_limit_sparse);
+  const bool skip_all = (!dense && q_row0 >= q_limit_sparse);
 
   // ---- stage the row mask in shared memory ----
   const int nwords = p.mask_words;
@@ -331,10 +337,12 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
 
     // ---- epilogue: O / l -> global (ref :135-136); rows past the limit are zeros (:156) ----
     const bool in_tensor = q_row < p.q_rows;
-    const bool zero_row = (n_tiles == 0) || (!dense && q_row >= p.q_limit_sparse);
+    const bool zero_row = (n_tiles == 0) || (!dense && q_row >= q_limit_sparse);
     const float inv_l = zero_row ? 0.f : 1.0f / l_sum;
-    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + b * p.o_stride_b + q_row * p.o_stride_s +
-                     static_cast<long long>(h) * p.o_stride_h;
+    const long long o_off =
+        b * p.o_stride_b + q_row * p.o_stride_s + static_cast<long long>(h) * p.o_stride_h;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + o_off;
+    float* orow32 = reinterpret_cast<float*>(p.out) + o_off;
 #pragma unroll 1
     for (int cc = 0; cc < 128; cc += 32) {
       uint32_t o[32];
@@ -356,7 +364,18 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
             const float bb = zero_row ? 0.f : __uint_as_float(o[i + 2 * t + 1]) * inv_l;
             e[t] = pack2<kBF16>(a, bb);
           }
-          *reinterpret_cast<uint4*>(orow + cc + i) = v;
+          if (!p.out_f32) {
+            *reinterpret_cast<uint4*>(orow + cc + i) = v;
+          } else {  // wan/…:530-532: the 16-bit result is widened back to the query dtype
+            float4 f0, f1;
+            float2 t0 = unpack2<kBF16>(e[0]), t1 = unpack2<kBF16>(e[1]);
+            f0 = make_float4(t0.x, t0.y, t1.x, t1.y);
+            t0 = unpack2<kBF16>(e[2]);
+            t1 = unpack2<kBF16>(e[3]);
+            f1 = make_float4(t0.x, t0.y, t1.x, t1.y);
+            *reinterpret_cast<float4*>(orow32 + cc + i) = f0;
+            *reinterpret_cast<float4*>(orow32 + cc + i + 4) = f1;
+          }
         }
       }
     }
@@ -417,6 +436,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
                                a->v_stride_h, a->o_stride_b, a->o_stride_s, a->o_stride_h};
   for (long long s : strides)
     if (!stride_ok(s)) return set_error(JENGA_E_INVALID, "strides must be positive multiples of 8");
+  if (a->out_dtype != a->dtype && a->out_dtype != JENGA_F32)
+    return set_error(JENGA_E_INVALID, "out_dtype must equal dtype or be f32");
   const uintptr_t ptrs[] = {(uintptr_t)a->q, (uintptr_t)a->k, (uintptr_t)a->v, (uintptr_t)a->out};
   for (uintptr_t q : ptrs)
     if (q % 16) return set_error(JENGA_E_INVALID, "pointers must be 16-byte aligned");
@@ -448,6 +469,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   p.qk_scale = static_cast<float>(static_cast<double>(a->sm_scale) * 1.44269504);  // ref :172
   p.text_amp = a->text_amp;
   p.mask_bits = a->mask_bits;
+  p.seqlen_dev = a->seqlen_dev;
+  p.out_f32 = a->out_dtype == JENGA_F32 ? 1 : 0;
   p.out = a->out;
   p.o_stride_b = a->o_stride_b;
   p.o_stride_s = a->o_stride_s;

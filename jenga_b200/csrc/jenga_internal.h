@@ -20,5 +20,10 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, v
                       CUtensorMapFloatOOBfill oob);
 
 int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream);
+int block_pool_impl(const void* x, void* pooled, void* cast_out, int in_dtype, int out_dtype,
+                    int batch, int heads, int head_dim, long long rows, long long sb, long long ss,
+                    long long sh, int n_blocks, cudaStream_t stream);
+int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream);
+int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream);
 
 }  // namespace jenga

@@ -1,0 +1,253 @@
+// Attention prologue for the HunyuanVideo DiT blocks: per-head RMSNorm(q,k) + RoPE(q,k on
+// image tokens) + img||txt concatenation + block mean-pool of q and k, in ONE pass over qkv.
+//
+// Replaces (hyvideo/modules/models_mul_block_gc_ha_multigpu.py:200-241, single-stream
+// :417-435) the chain  rearrange -> RMSNorm.forward (norm_layers.py:32-59) x4 ->
+// apply_rotary_emb (posemb_layers.py:181-229) -> torch.cat x3  (~16 elementwise kernels and
+// three 680 MB concatenation copies) and the two pooling reductions of the mask builder
+// (attention_block_triton_diffres.py:216-217).
+//
+// Rounding points reproduced exactly:
+//   n  = bf16( x_f32 * rsqrt(mean(x_f32^2) + eps) )          norm_layers.py:56  .type_as(x)
+//   y  = bf16( n * w )                                        :58  (bf16 x bf16 product)
+//   r  = bf16( y_f32*cos + rotate_half(y_f32)*sin )           posemb_layers.py:211-212
+//        with separate fp32 multiplies and add (no FMA contraction), interleaved pairs
+//        rotate_half(y)[2i] = -y[2i+1], [2i+1] = y[2i]        :133-137
+// Text tokens get the norm but no RoPE (:226-227).  v is copied unchanged.
+//
+// HBM-bound: reads qkv once (3*S*H*D*2 B) + cos/sin (2*L*D*4 B, L1/L2-shared by all heads),
+// writes q,k,v once.  One CTA per 128-token block; a half-warp owns one (token, head) row
+// (8 channels per lane), so the norm reduction is 4 shuffles and each lane keeps the pooling
+// partial sums of its own 8 channels across the 128 tokens of the block.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "sm100_ptx.cuh"
+#include "jenga_internal.h"
+
+namespace jenga {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+template <bool kBF16>
+__device__ __forceinline__ float rnd(float x) {
+  if constexpr (kBF16) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+  } else {
+    return __half2float(__float2half_rn(x));
+  }
+}
+
+struct PrologueParams {
+  // image and text qkv: [B, L, 3, H, D] views; element strides for (batch, token, which, head)
+  const uint16_t* img;
+  const uint16_t* txt;
+  long long img_sb, img_ss, img_sw, img_sh;
+  long long txt_sb, txt_ss, txt_sw, txt_sh;
+  int L, T, H;                  // image tokens, text tokens, heads (D == 128)
+  const uint16_t* w_img_q;      // [D] norm weights (may be null == ones)
+  const uint16_t* w_img_k;
+  const uint16_t* w_txt_q;
+  const uint16_t* w_txt_k;
+  const float* cos_t;           // [L or table rows, D] fp32
+  const float* sin_t;
+  const long long* rope_index;  // optional [L]: row of the table for token i (hilbert_order)
+  float eps;
+  uint16_t* q;                  // [B, S, H, D] contiguous, S = L + T
+  uint16_t* k;
+  uint16_t* v;
+  uint16_t* q_pool;             // [B, H, nb, D] or null
+  uint16_t* k_pool;
+  int nb;                       // ceil(S / 128)
+};
+
+template <bool kBF16>
+__device__ __forceinline__ void load8(const uint16_t* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack2<kBF16>(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <bool kBF16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack2<kBF16>(f[0], f[1]);
+  v.y = pack2<kBF16>(f[2], f[3]);
+  v.z = pack2<kBF16>(f[4], f[5]);
+  v.w = pack2<kBF16>(f[6], f[7]);
+  return v;
+}
+
+// x (8 channels of one head row, spread over 16 lanes) -> normed, weighted, optionally rotated;
+// values are left rounded to the 16-bit dtype (as floats).
+template <bool kBF16>
+__device__ __forceinline__ void norm_rope8(float (&x)[8], const float (&w)[8], bool has_w, float eps,
+                                           const float* cs, const float* sn, unsigned half_mask) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(half_mask, ss, o);
+  const float r = rsqrtf(ss * (1.0f / 128.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float n = rnd<kBF16>(__fmul_rn(x[i], r));
+    if (has_w) n = rnd<kBF16>(__fmul_rn(n, w[i]));
+    x[i] = n;
+  }
+  if (cs) {
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(cs) + 1);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sn) + 1);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      y[i] = rnd<kBF16>(__fadd_rn(__fmul_rn(x[i], c[i]), __fmul_rn(-x[i + 1], s[i])));
+      y[i + 1] = rnd<kBF16>(__fadd_rn(__fmul_rn(x[i + 1], c[i + 1]), __fmul_rn(x[i], s[i + 1])));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = y[i];
+  }
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(384)
+hy_prologue_kernel(const PrologueParams p) {
+  const int blk = blockIdx.x;
+  const int b = blockIdx.y;
+  const int S = p.L + p.T;
+  const int lane16 = threadIdx.x & 15;  // 8-channel chunk inside the head row
+  const int d0 = lane16 * 8;
+  const int rows_per_iter = blockDim.x >> 4;  // (token, head) rows handled per pass
+  const long long tok0 = static_cast<long long>(blk) * kBlock;
+  const int n_tok = static_cast<int>(min(static_cast<long long>(kBlock), S - tok0));
+
+  // A thread always serves the same head set {h : (h - hslot) % rows_per_iter == 0} so its
+  // pooling accumulators are per (head, chunk).  With H <= rows_per_iter (24 <= 24) that is
+  // exactly one head per half-warp and the block's 128 tokens are walked sequentially.
+  const int hslot = threadIdx.x >> 4;
+  // the two half-warps of a warp may serve different head counts: shuffle inside the half only
+  const unsigned half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+  for (int h = hslot; h < p.H; h += rows_per_iter) {
+    float wq_i[8], wk_i[8], wq_t[8], wk_t[8];
+    const bool has_w = p.w_img_q != nullptr;
+    if (has_w) {
+      load8<kBF16>(p.w_img_q + d0, wq_i);
+      load8<kBF16>(p.w_img_k + d0, wk_i);
+      load8<kBF16>(p.w_txt_q + d0, wq_t);
+      load8<kBF16>(p.w_txt_k + d0, wk_t);
+    }
+    float qsum[8], ksum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qsum[i] = ksum[i] = 0.f;
+#pragma unroll 2
+    for (int t = 0; t < n_tok; ++t) {
+      const long long tok = tok0 + t;
+      const bool is_img = tok < p.L;
+      const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
+                                   : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
+      const long long sw = is_img ? p.img_sw : p.txt_sw;
+      float q[8], k[8];
+      load8<kBF16>(src, q);
+      load8<kBF16>(src + sw, k);
+      const uint4 vraw = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
+      const float* cs = nullptr;
+      const float* sn = nullptr;
+      if (is_img && p.cos_t) {
+        const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
+        cs = p.cos_t + row * 128 + d0;
+        sn = p.sin_t + row * 128 + d0;
+      }
+      norm_rope8<kBF16>(q, is_img ? wq_i : wq_t, has_w, p.eps, cs, sn, half_mask);
+      norm_rope8<kBF16>(k, is_img ? wk_i : wk_t, has_w, p.eps, cs, sn, half_mask);
+      const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
+      *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
+      *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
+      *reinterpret_cast<uint4*>(p.v + o) = vraw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        qsum[i] += q[i];
+        ksum[i] += k[i];
+      }
+    }
+    if (p.q_pool) {
+      float qm[8], km[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        qm[i] = qsum[i] * (1.0f / kBlock);  // missing tail rows count as zeros (padding)
+        km[i] = ksum[i] * (1.0f / kBlock);
+      }
+      const long long o = ((static_cast<long long>(b) * p.H + h) * p.nb + blk) * 128 + d0;
+      *reinterpret_cast<uint4*>(p.q_pool + o) = pack8<kBF16>(qm);
+      *reinterpret_cast<uint4*>(p.k_pool + o) = pack8<kBF16>(km);
+    }
+  }
+}
+
+}  // namespace
+
+int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream) {
+  if (!a || !a->img_qkv || !a->q || !a->k || !a->v)
+    return set_error(JENGA_E_INVALID, "hy_prologue: null pointer");
+  if (a->dtype != JENGA_BF16 && a->dtype != JENGA_F16)
+    return set_error(JENGA_E_INVALID, "hy_prologue: dtype must be bf16/f16");
+  if (a->head_dim != 128) return set_error(JENGA_E_UNSUPPORTED, "hy_prologue: head_dim must be 128");
+  if (a->batch <= 0 || a->heads <= 0 || a->img_tokens <= 0 || a->txt_tokens < 0)
+    return set_error(JENGA_E_INVALID, "hy_prologue: bad shape");
+  if (a->txt_tokens > 0 && !a->txt_qkv) return set_error(JENGA_E_INVALID, "hy_prologue: txt_qkv missing");
+  const bool any_w = a->w_img_q || a->w_img_k || a->w_txt_q || a->w_txt_k;
+  const bool all_w = a->w_img_q && a->w_img_k && (a->txt_tokens == 0 || (a->w_txt_q && a->w_txt_k));
+  if (any_w && !all_w) return set_error(JENGA_E_INVALID, "hy_prologue: give all norm weights or none");
+  if ((a->rope_cos == nullptr) != (a->rope_sin == nullptr))
+    return set_error(JENGA_E_INVALID, "hy_prologue: cos and sin go together");
+  if ((a->q_pool == nullptr) != (a->k_pool == nullptr))
+    return set_error(JENGA_E_INVALID, "hy_prologue: q_pool and k_pool go together");
+  const long long st[] = {a->img_stride_b, a->img_stride_s, a->img_stride_w, a->img_stride_h,
+                          a->txt_stride_b, a->txt_stride_s, a->txt_stride_w, a->txt_stride_h};
+  for (long long s : st)
+    if (s % 8) return set_error(JENGA_E_INVALID, "hy_prologue: strides must be multiples of 8 elements");
+  PrologueParams p{};
+  p.img = static_cast<const uint16_t*>(a->img_qkv);
+  p.txt = static_cast<const uint16_t*>(a->txt_qkv);
+  p.img_sb = a->img_stride_b; p.img_ss = a->img_stride_s; p.img_sw = a->img_stride_w; p.img_sh = a->img_stride_h;
+  p.txt_sb = a->txt_stride_b; p.txt_ss = a->txt_stride_s; p.txt_sw = a->txt_stride_w; p.txt_sh = a->txt_stride_h;
+  p.L = static_cast<int>(a->img_tokens);
+  p.T = static_cast<int>(a->txt_tokens);
+  p.H = a->heads;
+  p.w_img_q = static_cast<const uint16_t*>(a->w_img_q);
+  p.w_img_k = static_cast<const uint16_t*>(a->w_img_k);
+  p.w_txt_q = static_cast<const uint16_t*>(a->w_txt_q ? a->w_txt_q : a->w_img_q);
+  p.w_txt_k = static_cast<const uint16_t*>(a->w_txt_k ? a->w_txt_k : a->w_img_k);
+  p.cos_t = a->rope_cos;
+  p.sin_t = a->rope_sin;
+  p.rope_index = reinterpret_cast<const long long*>(a->rope_index);
+  p.eps = a->eps;
+  p.q = static_cast<uint16_t*>(a->q);
+  p.k = static_cast<uint16_t*>(a->k);
+  p.v = static_cast<uint16_t*>(a->v);
+  p.q_pool = static_cast<uint16_t*>(a->q_pool);
+  p.k_pool = static_cast<uint16_t*>(a->k_pool);
+  const long long S = a->img_tokens + a->txt_tokens;
+  p.nb = static_cast<int>((S + kBlock - 1) / kBlock);
+  dim3 grid(p.nb, a->batch);
+  int threads = a->heads * 16;
+  if (threads > 384) threads = 384;
+  threads = ((threads + 31) / 32) * 32;
+  if (a->dtype == JENGA_BF16)
+    hy_prologue_kernel<true><<<grid, threads, 0, stream>>>(p);
+  else
+    hy_prologue_kernel<false><<<grid, threads, 0, stream>>>(p);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "hy_prologue launch");
+}
+
+}  // namespace jenga

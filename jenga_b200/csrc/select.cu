@@ -1,0 +1,404 @@
+// Block scoring and selection — the device-side replacement of the reference's
+// _build_block_index_with_importance_optimized
+//   (hyvideo/modules/attention_block_triton_diffres.py:198-295, wan twin :306-411).
+//
+// The reference strings ~25 ATen kernels together (mean, bmm, softmax, sort, cumsum, four
+// boolean-mask gathers that each synchronise with the host, index_put, OR) and materialises a
+// [B,H,nq,nb] bool tensor.  Here it is two kernels, no host sync, and the result is the packed
+// bit rows the attention kernel consumes:
+//   block_pool_kernel   : HBM-bound mean over each 128-token block (one read of q and k)
+//   select_blocks_kernel: per (head, 8 query blocks): pooled scores -> fp32 softmax -> full
+//                         descending sort (ties: lower index first, like CUDA torch.sort) ->
+//                         cumulative-probability cut -> max(count, top_k) -> union with
+//                         neighbour / first-frame / text columns -> bit row
+// Rounding points follow the reference under torch.autocast(bf16):
+// pooled means, the pooled dot products and their product with D^-1/2 are each rounded to the
+// input dtype; softmax and the cumulative sum are fp32.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "sm100_ptx.cuh"
+#include "jenga_internal.h"
+
+namespace jenga {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+template <int kDtype>
+__device__ __forceinline__ float round_to(float x) {
+  if constexpr (kDtype == JENGA_BF16) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+  } else {
+    return __half2float(__float2half_rn(x));
+  }
+}
+template <int kDtype>
+__device__ __forceinline__ uint16_t to_bits16(float x) {
+  if constexpr (kDtype == JENGA_BF16) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  } else {
+    return __half_as_ushort(__float2half_rn(x));
+  }
+}
+template <int kDtype>
+__device__ __forceinline__ float from_bits16(uint16_t v) {
+  if constexpr (kDtype == JENGA_BF16) {
+    return __uint_as_float(static_cast<uint32_t>(v) << 16);
+  } else {
+    return __half2float(__ushort_as_half(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// block_pool: pooled[b,h,blk,:] = round(mean over the 128 rows of the block), rows >= S count
+// as zeros (the Wan / I2V variants zero-pad before pooling, wan/…:448-451).
+// ref :216-217.  kIn: element type of x (bf16, f16 or f32).  With f32 input every element is
+// first rounded to bf16 (wan/…:456-463 casts before the builder runs) and, if cast_out is
+// given, the rounded copy is written contiguously as [B,S,H,D] bf16.
+// grid: (block, batch); thread -> 8 consecutive channels of one head.
+// ------------------------------------------------------------------------------------------
+template <int kIn, int kOut>
+__global__ void __launch_bounds__(256)
+block_pool_kernel(const void* __restrict__ x, uint16_t* __restrict__ pooled,
+                  uint16_t* __restrict__ cast_out, int heads, int head_dim, long long rows,
+                  long long sb, long long ss, long long sh, int n_blocks) {
+  const int blk = blockIdx.x;
+  const int b = blockIdx.y;
+  const int vec_per_head = head_dim / 8;
+  const int vecs = heads * vec_per_head;
+  const long long row0 = static_cast<long long>(blk) * kBlock;
+  const int n_rows = static_cast<int>(min(static_cast<long long>(kBlock), rows - row0));
+  for (int vidx = threadIdx.x; vidx < vecs; vidx += blockDim.x) {
+    const int h = vidx / vec_per_head;
+    const int d0 = (vidx - h * vec_per_head) * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if constexpr (kIn == JENGA_F32) {
+      const float* base = static_cast<const float*>(x) + b * sb + h * sh + d0;
+#pragma unroll 4
+      for (int r = 0; r < n_rows; ++r) {
+        const float4* p = reinterpret_cast<const float4*>(base + (row0 + r) * ss);
+        const float4 lo = __ldg(p), hi = __ldg(p + 1);
+        const float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint16_t o16[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o16[i] = to_bits16<kOut>(f[i]);
+          acc[i] += from_bits16<kOut>(o16[i]);
+        }
+        if (cast_out) {
+          uint4 v;
+          v.x = o16[0] | (static_cast<uint32_t>(o16[1]) << 16);
+          v.y = o16[2] | (static_cast<uint32_t>(o16[3]) << 16);
+          v.z = o16[4] | (static_cast<uint32_t>(o16[5]) << 16);
+          v.w = o16[6] | (static_cast<uint32_t>(o16[7]) << 16);
+          *reinterpret_cast<uint4*>(cast_out + ((static_cast<long long>(b) * rows + row0 + r) * heads + h) *
+                                                   head_dim + d0) = v;
+        }
+      }
+    } else {
+      const uint16_t* base = static_cast<const uint16_t*>(x) + b * sb + h * sh + d0;
+#pragma unroll 8
+      for (int r = 0; r < n_rows; ++r) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ss));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += from_bits16<kIn>(static_cast<uint16_t>(w[i] & 0xffffu));
+          acc[2 * i + 1] += from_bits16<kIn>(static_cast<uint16_t>(w[i] >> 16));
+        }
+      }
+    }
+    uint16_t o16[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o16[i] = to_bits16<kOut>(acc[i] * (1.0f / kBlock));
+    uint4 v;
+    v.x = o16[0] | (static_cast<uint32_t>(o16[1]) << 16);
+    v.y = o16[2] | (static_cast<uint32_t>(o16[3]) << 16);
+    v.z = o16[4] | (static_cast<uint32_t>(o16[5]) << 16);
+    v.w = o16[6] | (static_cast<uint32_t>(o16[7]) << 16);
+    *reinterpret_cast<uint4*>(pooled + ((static_cast<long long>(b) * heads + h) * n_blocks + blk) * head_dim +
+                              d0) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// select_blocks
+// ------------------------------------------------------------------------------------------
+struct SelectParams {
+  const uint16_t* q_pool;  // [BH, nq, D]
+  const uint16_t* k_pool;  // [BH, nk_pool, D]  (first n_img rows are used)
+  int nk_pool;
+  int head_dim;
+  int nq;           // query blocks (image rows)
+  int n_img;        // ranked key blocks == text_start_block
+  int nb;           // all key blocks (bit row covers these)
+  int words;        // bit-row pitch
+  int top_k;
+  float p_threshold;
+  int text_blocks;
+  int first_frame_blocks;
+  const uint32_t* nbr_bits;  // [nbr_rows, nbr_words] or null
+  int nbr_rows, nbr_words;
+  uint32_t* out_bits;  // [BH, nq, words]
+  int32_t* out_counts;  // [BH, nq] importance count n (before unions), may be null
+  int rows_per_cta;
+  int npow2;  // sort width
+};
+
+// Warp-cooperative bitonic sort, descending, of n2 (power of two) 64-bit keys in shared memory.
+__device__ void warp_bitonic_desc(unsigned long long* keys, int n2, int lane) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n2; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool desc_seg = (i & k) == 0;
+          if (desc_seg ? (a < b) : (a > b)) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int kDtype>
+__global__ void __launch_bounds__(256)
+select_blocks_kernel(const SelectParams p) {
+  extern __shared__ uint8_t smem_sel[];
+  const int R = p.rows_per_cta;
+  const int D = p.head_dim;
+  // carve: q rows fp32 [R][D] | scores fp32 [R][n_img] | keys u64 [R][npow2] | bits [R][words]
+  float* s_q = reinterpret_cast<float*>(smem_sel);
+  float* s_sc = s_q + R * D;
+  unsigned long long* s_keys =
+      reinterpret_cast<unsigned long long*>(s_sc + ((R * p.n_img + 1) & ~1));
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_keys + static_cast<size_t>(R) * p.npow2);
+
+  const int groups = (p.nq + R - 1) / R;
+  const int bh = blockIdx.x / groups;
+  const int m0 = (blockIdx.x - bh * groups) * R;
+  const int nrows = min(R, p.nq - m0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+
+  // ---- pooled q rows -> fp32 shared
+  for (int i = threadIdx.x; i < nrows * D; i += blockDim.x) {
+    const int r = i / D, d = i - r * D;
+    s_q[i] = from_bits16<kDtype>(p.q_pool[(static_cast<size_t>(bh) * p.nq + m0 + r) * D + d]);
+  }
+  for (int i = threadIdx.x; i < R * p.words; i += blockDim.x) s_bits[i] = 0;
+  __syncthreads();
+
+  // ---- scores: s[r][j] = round(round(q_r . k_j) * D^-1/2)     (ref :227)
+  const float inv_sqrt_d = static_cast<float>(1.0 / sqrt(static_cast<double>(D)));
+  for (int j = threadIdx.x; j < p.n_img; j += blockDim.x) {
+    const uint4* krow =
+        reinterpret_cast<const uint4*>(p.k_pool + (static_cast<size_t>(bh) * p.nk_pool + j) * D);
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int d8 = 0; d8 < D / 8; ++d8) {
+      const uint4 v = __ldg(krow + d8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float kf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        kf[2 * i] = from_bits16<kDtype>(static_cast<uint16_t>(w[i] & 0xffffu));
+        kf[2 * i + 1] = from_bits16<kDtype>(static_cast<uint16_t>(w[i] >> 16));
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r < nrows) {
+          const float* qr = s_q + r * D + d8 * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r] = fmaf(qr[i], kf[i], acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < nrows) s_sc[r * p.n_img + j] = round_to<kDtype>(round_to<kDtype>(acc[r]) * inv_sqrt_d);
+  }
+  __syncthreads();
+
+  // ---- one warp per row: softmax, sort, cut, unions
+  for (int r = warp; r < nrows; r += nwarps) {
+    const int m = m0 + r;
+    float* sc = s_sc + r * p.n_img;
+    unsigned long long* keys = s_keys + static_cast<size_t>(r) * p.npow2;
+    uint32_t* bits = s_bits + r * p.words;
+    // softmax in fp32 (ref :238; autocast promotes softmax to fp32)
+    float mx = -INFINITY;
+    for (int j = lane; j < p.n_img; j += 32) mx = fmaxf(mx, sc[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < p.n_img; j += 32) {
+      const float e = expf(sc[j] - mx);
+      sc[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    // keys: (prob bits, ~index) so that a descending sort puts equal probs in index order
+    for (int j = lane; j < p.npow2; j += 32) {
+      unsigned long long key = 0ull;
+      if (j < p.n_img) {
+        const float pr = sc[j] / sum;
+        sc[j] = pr;
+        key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) |
+              static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(j));
+      }
+      keys[j] = key;  // padding keys are 0 -> sort to the end
+    }
+    __syncwarp();
+    warp_bitonic_desc(keys, p.npow2, lane);
+    // cumulative probability in sorted order (ref :242-246): count = #(cumsum <= p) + 1.
+    // cumsum of non-negative terms is monotone, so this is the first index that exceeds p.
+    // Warp-parallel: each lane sums a contiguous chunk, chunks are combined in order.
+    int count;
+    {
+      const int per = (p.n_img + 31) / 32;
+      const int lo = lane * per, hi = min(p.n_img, lo + per);
+      float part = 0.f;
+      for (int i = lo; i < hi; ++i) part += __uint_as_float(static_cast<uint32_t>(keys[i] >> 32));
+      float prefix = part;  // inclusive scan over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, prefix, o);
+        if (lane >= o) prefix += t;
+      }
+      float run = prefix - part;  // exclusive prefix of this lane's chunk
+      int local = 0;              // #elements in my chunk with cumsum <= p
+      for (int i = lo; i < hi; ++i) {
+        run += __uint_as_float(static_cast<uint32_t>(keys[i] >> 32));
+        if (run <= p.p_threshold) ++local;
+      }
+      int tot = local;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      count = tot + 1;
+    }
+    int n = max(count, p.top_k);  // ref :247-250
+    n = min(n, p.n_img);
+    for (int i = lane; i < n; i += 32) {
+      const uint32_t idx = 0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffull);
+      atomicOr(&bits[idx >> 5], 1u << (idx & 31));
+    }
+    __syncwarp();
+    // unions (ref :280-293, wan :400-406); all restricted to the columns they address
+    for (int w = lane; w < p.words; w += 32) {
+      uint32_t v = bits[w];
+      const int lo = w * 32;
+      auto range_bits = [&](int a, int b) -> uint32_t {  // bits of [a,b) that fall in word w
+        const int s = max(a, lo), e = min(b, lo + 32);
+        if (e <= s) return 0u;
+        const uint32_t hi_mask = (e - lo) >= 32 ? 0xffffffffu : ((1u << (e - lo)) - 1u);
+        return hi_mask & ~((s - lo) > 0 ? ((1u << (s - lo)) - 1u) : 0u);
+      };
+      if (p.nbr_bits && m < p.nbr_rows && w < p.nbr_words)
+        v |= p.nbr_bits[static_cast<size_t>(m) * p.nbr_words + w] & range_bits(0, p.n_img);
+      if (m < p.first_frame_blocks) v |= range_bits(0, min(p.first_frame_blocks, p.nb));
+      if (p.text_blocks > 0) v |= range_bits(p.n_img, min(p.n_img + p.text_blocks, p.nb));
+      p.out_bits[(static_cast<size_t>(bh) * p.nq + m) * p.words + w] = v;
+    }
+    if (p.out_counts && lane == 0) p.out_counts[static_cast<size_t>(bh) * p.nq + m] = n;
+  }
+}
+
+}  // namespace
+
+int block_pool_impl(const void* x, void* pooled, void* cast_out, int in_dtype, int out_dtype,
+                    int batch, int heads, int head_dim, long long rows, long long sb, long long ss,
+                    long long sh, int n_blocks, cudaStream_t stream) {
+  if (!x || !pooled) return set_error(JENGA_E_INVALID, "block_pool: null pointer");
+  if (batch <= 0 || heads <= 0 || head_dim <= 0 || head_dim % 8 || rows <= 0 || n_blocks <= 0)
+    return set_error(JENGA_E_INVALID, "block_pool: bad shape");
+  if (static_cast<long long>(n_blocks - 1) * kBlock >= rows)
+    return set_error(JENGA_E_INVALID, "block_pool: n_blocks beyond the rows");
+  const int esz = in_dtype == JENGA_F32 ? 4 : 2;
+  if ((sb * esz) % 16 || (ss * esz) % 16 || (sh * esz) % 16 || reinterpret_cast<uintptr_t>(x) % 16 ||
+      reinterpret_cast<uintptr_t>(pooled) % 16)
+    return set_error(JENGA_E_INVALID, "block_pool: 16-byte alignment required");
+  if (out_dtype != JENGA_BF16 && out_dtype != JENGA_F16)
+    return set_error(JENGA_E_INVALID, "block_pool: pooled dtype must be bf16/f16");
+  if (in_dtype != JENGA_F32 && in_dtype != out_dtype)
+    return set_error(JENGA_E_INVALID, "block_pool: 16-bit input must match the pooled dtype");
+  if (in_dtype == JENGA_F32 && out_dtype != JENGA_BF16)
+    return set_error(JENGA_E_UNSUPPORTED, "block_pool: f32 input is rounded to bf16 only");
+  dim3 grid(n_blocks, batch);
+  const int vecs = heads * head_dim / 8;
+  const int threads = vecs >= 256 ? 256 : ((vecs + 31) / 32) * 32;
+  uint16_t* po = static_cast<uint16_t*>(pooled);
+  uint16_t* co = static_cast<uint16_t*>(cast_out);
+  if (in_dtype == JENGA_F32)
+    block_pool_kernel<JENGA_F32, JENGA_BF16><<<grid, threads, 0, stream>>>(x, po, co, heads, head_dim, rows, sb, ss, sh, n_blocks);
+  else if (in_dtype == JENGA_BF16)
+    block_pool_kernel<JENGA_BF16, JENGA_BF16><<<grid, threads, 0, stream>>>(x, po, nullptr, heads, head_dim, rows, sb, ss, sh, n_blocks);
+  else
+    block_pool_kernel<JENGA_F16, JENGA_F16><<<grid, threads, 0, stream>>>(x, po, nullptr, heads, head_dim, rows, sb, ss, sh, n_blocks);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "block_pool launch");
+}
+
+int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream) {
+  if (!a || !a->q_pool || !a->k_pool || !a->out_bits)
+    return set_error(JENGA_E_INVALID, "select_blocks: null pointer");
+  if (a->dtype != JENGA_BF16 && a->dtype != JENGA_F16)
+    return set_error(JENGA_E_INVALID, "select_blocks: dtype must be bf16/f16");
+  if (a->batch_heads <= 0 || a->nq <= 0 || a->n_img <= 0 || a->nb < a->n_img ||
+      a->nk_pool < a->n_img || a->head_dim <= 0 || a->head_dim % 8)
+    return set_error(JENGA_E_INVALID, "select_blocks: bad shape");
+  if (a->mask_words * 32 < a->nb) return set_error(JENGA_E_INVALID, "select_blocks: mask_words too small");
+  if (a->top_k < 0 || a->text_blocks < 0 || a->first_frame_blocks < 0)
+    return set_error(JENGA_E_INVALID, "select_blocks: negative count");
+  int npow2 = 32;
+  while (npow2 < a->n_img) npow2 <<= 1;
+  auto smem_for = [&](int R) -> size_t {
+    return static_cast<size_t>(R) * a->head_dim * 4 + static_cast<size_t>((R * a->n_img + 1) & ~1) * 4 +
+           static_cast<size_t>(R) * npow2 * 8 + static_cast<size_t>(R) * a->mask_words * 4;
+  };
+  int R = 8;
+  while (R > 1 && smem_for(R) > 200 * 1024) R >>= 1;
+  if (smem_for(R) > 220 * 1024)
+    return set_error(JENGA_E_UNSUPPORTED, "select_blocks: %d key blocks exceed the shared-memory sort", a->n_img);
+  SelectParams p{};
+  p.q_pool = static_cast<const uint16_t*>(a->q_pool);
+  p.k_pool = static_cast<const uint16_t*>(a->k_pool);
+  p.nk_pool = a->nk_pool;
+  p.head_dim = a->head_dim;
+  p.nq = a->nq;
+  p.n_img = a->n_img;
+  p.nb = a->nb;
+  p.words = a->mask_words;
+  p.top_k = a->top_k;
+  p.p_threshold = a->p_threshold;
+  p.text_blocks = a->text_blocks;
+  p.first_frame_blocks = a->first_frame_blocks;
+  p.nbr_bits = a->nbr_bits;
+  p.nbr_rows = a->nbr_rows;
+  p.nbr_words = a->nbr_words;
+  p.out_bits = a->out_bits;
+  p.out_counts = a->out_counts;
+  p.rows_per_cta = R;
+  p.npow2 = npow2;
+  const size_t smem = smem_for(R);
+  const long long groups = (a->nq + R - 1) / R;
+  const long long grid = groups * a->batch_heads;
+  auto kern = a->dtype == JENGA_BF16 ? select_blocks_kernel<JENGA_BF16> : select_blocks_kernel<JENGA_F16>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(select_blocks)");
+  kern<<<static_cast<unsigned>(grid), 256, smem, stream>>>(p);
+  ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "select_blocks launch");
+}
+
+}  // namespace jenga

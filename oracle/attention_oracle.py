@@ -168,6 +168,7 @@ def block_sparse_attention(
     max_seqlen_q=None, max_seqlen_kv=None, text_blocks: int = 2, text_amp: float = 0.0,
     block_neighbor_list=None, shape_xfuse: bool = False, p_remain_rates: float = 0.5,
     first_frame_blocks: int = 0, variant: str = "hyvideo", return_mask: bool = False,
+    mask_override: torch.Tensor | None = None,
 ):
     """The whole operator, [B,S,H,D] in -> [B,S,H*D] out.
     variant "hyvideo": …/hyvideo/modules/attention_block_triton_diffres.py:298-424
@@ -180,14 +181,13 @@ def block_sparse_attention(
     v = value.transpose(1, 2)
     B, H, S, D = q.shape
     use_cu = cu_seqlens_q is not None and cu_seqlens_kv is not None and variant != "wan"
+    pad = (128 - S % 128) % 128
     if use_cu:
         seqlen = int(cu_seqlens_q[1])                                              # :328-329
-        pad = 0
     else:
-        pad = (128 - S % 128) % 128
         seqlen = S
-    if variant == "hyvideo" and not use_cu:
-        pad = 0  # the HunyuanVideo variant computes padded copies but never uses them (:331-335)
+    if variant == "hyvideo":
+        pad = 0  # the HunyuanVideo variant never pads (:327-335); the I2V one does (:323-328)
     if pad:
         q = torch.nn.functional.pad(q, [0, 0, 0, pad])
         k = torch.nn.functional.pad(k, [0, 0, 0, pad])
@@ -203,8 +203,9 @@ def block_sparse_attention(
     mask = None
     if normal_blocks > 0:
         qn = q[:, :, :normal_tokens]
-        mask = build_block_onehot(qn, k, top_k, normal_blocks, num_blocks, p_remain_rates,
-                                  text_blocks, block_neighbor_list, first_frame_blocks)
+        mask = mask_override if mask_override is not None else build_block_onehot(
+            qn, k, top_k, normal_blocks, num_blocks, p_remain_rates, text_blocks,
+            block_neighbor_list, first_frame_blocks)
         outs.append(carved_attention_rows(qn, k, v, mask, seqlen, sm_scale, text_amp,
                                           normal_blocks))
     if text_blocks > 0:

@@ -162,8 +162,49 @@ def mask_goldens():
     np.savez_compressed(OUT / "mask_builder.npz", **out)
 
 
+# ----------------------------------------------------------------------------- prologue (a-5, a-6)
+def prologue_goldens():
+    """RMSNorm + apply_rotary_emb exactly as MMDoubleStreamBlock.forward chains them
+    (models_mul_block_gc_ha_multigpu.py:200-241), using the reference modules imported by path
+    and its own RoPE table builder (theta 256, dims [16,56,56])."""
+    import synth
+    from einops import rearrange
+    norm = _import("ref_norm_layers", REF / "hyvideo/modules/norm_layers.py")
+    pos = _import("ref_posemb_layers", REF / "hyvideo/modules/posemb_layers.py")
+    c = synth.prologue_case()
+    H = c["H"]
+    cos, sin = pos.get_nd_rotary_pos_embed([16, 56, 56], list(c["grid"]), theta=256, use_real=True,
+                                           theta_rescale_factor=1)
+    l2h = torch.randperm(c["L"], generator=torch.Generator().manual_seed(3))  # stands in for hilbert_order
+    cos_g, sin_g = cos[l2h], sin[l2h]
+
+    def mk(w):
+        m = norm.RMSNorm(128, elementwise_affine=True, eps=1e-6, dtype=torch.bfloat16)
+        with torch.no_grad():
+            m.weight.copy_(w)
+        return m
+
+    iq, ik, iv = rearrange(c["img"], "B L (K H D) -> K B L H D", K=3, H=H)
+    tq, tk, tv = rearrange(c["txt"], "B L (K H D) -> K B L H D", K=3, H=H)
+    with torch.no_grad():
+        iq = mk(c["w_img_q"])(iq).to(iv)
+        ik = mk(c["w_img_k"])(ik).to(iv)
+        iq, ik = pos.apply_rotary_emb(iq, ik, (cos_g, sin_g), head_first=False)
+        tq = mk(c["w_txt_q"])(tq).to(tv)
+        tk = mk(c["w_txt_k"])(tk).to(tv)
+    q = torch.cat((iq, tq), dim=1)
+    k = torch.cat((ik, tk), dim=1)
+    v = torch.cat((iv, tv), dim=1)
+    np.savez_compressed(OUT / "prologue.npz", q=q.view(torch.int16).numpy(), k=k.view(torch.int16).numpy(),
+                        v_sha=np.frombuffer(sha16(v.contiguous().view(torch.int16).numpy()).encode(), dtype=np.uint8),
+                        cos=cos.numpy(), sin=sin.numpy(), index=l2h.numpy())
+    print("prologue", q.shape, float(q.float().abs().mean()), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gilbert", "attention", "mask"]
+    which = sys.argv[1:] or ["gilbert", "attention", "mask", "prologue"]
+    if "prologue" in which:
+        prologue_goldens()
     if "gilbert" in which:
         gilbert_goldens()
     if "attention" in which:

@@ -115,3 +115,18 @@ def mask_case(name):
         return dict(variant=variant, H=H, n_img=n_img, n_txt=n_txt, top_k=top_k, p=p, ff=ff, q=q,
                     k=k, nbr=nbr)
     raise KeyError(name)
+
+
+PROLOGUE_CASE = dict(grid=(4, 8, 8), T=64, H=3, seed=41)  # L = 256 image tokens + 64 text tokens
+
+
+def prologue_case():
+    """img/txt fused-QKV activations [1, tokens, 3*H*128] bf16 and norm weights [128] bf16."""
+    c = PROLOGUE_CASE
+    t, h, w = c["grid"]
+    L, T, H = t * h * w, c["T"], c["H"]
+    img = (1.5 * normal((1, L, 3 * H * 128), c["seed"])).bfloat16()
+    txt = (0.7 * normal((1, T, 3 * H * 128), c["seed"] + 1)).bfloat16()
+    ws = [(1.0 + 0.2 * normal((128,), c["seed"] + 2 + i)).bfloat16() for i in range(4)]
+    return dict(L=L, T=T, H=H, grid=c["grid"], img=img, txt=txt, w_img_q=ws[0], w_img_k=ws[1],
+                w_txt_q=ws[2], w_txt_k=ws[3])
