@@ -1,0 +1,196 @@
+"""Ulysses sequence parallelism around the carved-attention operator (one box, NVLink/NVSwitch).
+
+Drop-in for the reference's SP wrapper
+  hyvideo/modules/xdit_ring_atten.py:61-222  xFuserLongContextAttention.forward
+  hyvideo/modules/attenion.py:159-195        my_parallel_attention
+Outside attention each rank owns a contiguous 1/P slice of the curve-ordered image tokens and
+a replica of the text tokens; inside, rank r owns heads [r*H/P, (r+1)*H/P) over the whole
+sequence.  Data movement:
+  in : Q, K, V image rows   all-to-all (scatter heads, gather sequence)       — 3 collectives
+       text Q/K/V           local head slice (the reference's text-Q all-to-all returns
+                            exactly that slice, :129-131 — no exchange needed)
+  out: image rows           all-to-all (scatter sequence, gather heads)       — 1 collective
+       text rows            all-gather over heads (the reference repeats the rows P times and
+                            all-to-alls them, :207,:215-217 — same result)
+Collectives are NCCL via torch.distributed (`gloo` works for the CPU tests of the layout
+logic); the attention itself is the single-GPU operator on the rank's head group.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+BLOCK = 128
+
+
+def _group_size_rank(group):
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def seq_to_heads(x: torch.Tensor, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B, n_loc, H, D] (all heads, my token slice) -> [B, P*n_loc, H/P, D] (my heads, all
+    tokens, slices concatenated in rank order).  == SeqAllToAll4D(scatter_idx=2, gather_idx=1)."""
+    P, _ = _group_size_rank(group)
+    B, n, H, D = x.shape
+    assert H % P == 0, "heads must divide by the SP degree"
+    h = H // P
+    send = x.reshape(B, n, P, h, D).permute(2, 0, 1, 3, 4).contiguous()  # [P, B, n, h, D]
+    if B == 1 and out is not None and out.is_contiguous():
+        # rank-order concatenation along the sequence IS the receive layout: land in place
+        dist.all_to_all_single(out.view(P, 1, n, h, D), send, group=group)
+        return out
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    y = recv.permute(1, 0, 2, 3, 4).reshape(B, P * n, h, D)  # view when B == 1
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def heads_to_seq(x: torch.Tensor, group=None) -> torch.Tensor:
+    """[B, P*n_loc, H/P, D] -> [B, n_loc, H, D].  == SeqAllToAll4D(scatter_idx=1, gather_idx=2)."""
+    P, _ = _group_size_rank(group)
+    B, N, h, D = x.shape
+    assert N % P == 0
+    n = N // P
+    send = x.reshape(B, P, n, h, D).permute(1, 0, 2, 3, 4).contiguous()  # [P, B, n, h, D]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 2, 0, 3, 4).reshape(B, n, P * h, D)
+
+
+def gather_heads(x: torch.Tensor, group=None) -> torch.Tensor:
+    """[B, T, H/P, D] on every rank (different head groups) -> [B, T, H, D] everywhere."""
+    P, _ = _group_size_rank(group)
+    B, T, h, D = x.shape
+    recv = torch.empty((P * B, T, h, D), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(recv, x.contiguous(), group=group)
+    return recv.view(P, B, T, h, D).permute(1, 2, 0, 3, 4).reshape(B, T, P * h, D)
+
+
+class UlyssesCarvedAttention:
+    """Callable with the signature the DiT blocks use for `hybrid_seq_parallel_attn`
+    (xdit_ring_atten.py:61-85).  `attn_fn` is injectable so the CPU tests can exercise the
+    layout logic with the oracle; by default it is the sm_100a operator."""
+
+    def __init__(self, group=None, attn_fn=None):
+        self.group = group
+        self._attn_fn = attn_fn
+
+    def _attn(self, *a, **k):
+        if self._attn_fn is None:
+            from .attention import block_sparse_attention
+            self._attn_fn = block_sparse_attention
+        return self._attn_fn(*a, **k)
+
+    def __call__(self, attn, query, key, value, *, joint_tensor_query=None, joint_tensor_key=None,
+                 joint_tensor_value=None, joint_strategy="none", top_k=0, text_amp=0.0,
+                 block_neighbor_list=None, p_remain_rates=0.0, cu_seqlens_q=None, cu_seqlens_kv=None,
+                 **_unused):
+        P, r = _group_size_rank(self.group)
+        B, q_len, H, D = query.shape
+        h = H // P
+        joint = joint_tensor_query is not None
+        if joint and joint_strategy != "rear":
+            # the reference also implements "front"; Jenga's blocks only ever pass "rear"
+            raise ValueError("only joint_strategy='rear' is built (attenion.py:181)")
+        if joint != (joint_tensor_key is not None) or joint != (joint_tensor_value is not None):
+            raise ValueError("joint_tensor_query/key/value must be given together")
+        T = joint_tensor_query.shape[1] if joint else 0
+        N = P * q_len
+        dev, dt = query.device, query.dtype
+        # receive buffers already shaped [B, N+T, h, D] so text rows are appended in place
+        qkv = [torch.empty((B, N + T, h, D), dtype=dt, device=dev) for _ in range(3)]
+        for buf, x in zip(qkv, (query, key, value)):
+            seq_to_heads(x, self.group, out=buf[:, :N])
+        if joint:
+            sl = slice(r * h, (r + 1) * h)
+            qkv[0][:, N:] = joint_tensor_query[:, :, sl]
+            qkv[1][:, N:] = joint_tensor_key[:, :, sl]
+            qkv[2][:, N:] = joint_tensor_value[:, :, sl]
+        # ref :183-184 — cu_seqlens = [0, txt_len + P*q_len, S]; txt_len = cu_seqlens_q[1] - q_len.
+        # Stays on the device (the reference's torch.tensor([...]) forces a host sync here).
+        if cu_seqlens_q is not None:
+            valid = (cu_seqlens_q[1:2].to(device=dev, dtype=torch.int32) - q_len) + N
+            cu = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), valid,
+                            torch.full((1,), N + T, dtype=torch.int32, device=dev)])
+        else:
+            cu = None
+        out = self._attn(qkv[0], qkv[1], qkv[2], top_k=top_k, block_size_M=128, block_size_N=128,
+                         cu_seqlens_q=cu, cu_seqlens_kv=cu, text_amp=text_amp,
+                         block_neighbor_list=block_neighbor_list, p_remain_rates=p_remain_rates,
+                         shape_xfuse=True, **({"text_blocks": T // BLOCK} if joint else {"text_blocks": 0}))
+        img = heads_to_seq(out[:, :N], self.group)
+        if not joint:
+            return img
+        txt = gather_heads(out[:, N:], self.group)
+        return torch.cat([img, txt], dim=1)
+
+
+def my_parallel_attention(hybrid_seq_parallel_attn, q, k, v, img_q_len, img_kv_len, cu_seqlens_q,
+                          cu_seqlens_kv, top_k=int(10e7), text_amp=0.0, block_neighbor_list=None,
+                          p_remain_rates=0.0):
+    """attenion.py:159-195, verbatim contract: q,k,v are img||txt per rank; returns [B, s, H*D]."""
+    attn = hybrid_seq_parallel_attn(
+        None, q[:, :img_q_len], k[:, :img_kv_len], v[:, :img_kv_len],
+        joint_tensor_query=q[:, img_q_len:], joint_tensor_key=k[:, img_kv_len:],
+        joint_tensor_value=v[:, img_kv_len:], joint_strategy="rear", top_k=top_k,
+        cu_seqlens_q=cu_seqlens_q, cu_seqlens_kv=cu_seqlens_kv, text_amp=text_amp,
+        block_neighbor_list=block_neighbor_list, p_remain_rates=p_remain_rates)
+    b, s, a, d = attn.shape
+    return attn.reshape(b, s, -1)
+
+
+# --------------------------------------------------------------------------------------------
+# bench.py helpers (N > 1): every rank builds ITS slice of the same global layer input
+# --------------------------------------------------------------------------------------------
+def bench_setup(wl, build_inputs, dev, rank, world):
+    full = build_inputs(wl, dev)  # identical seeds on every rank -> identical global tensors
+    n_img = full["n_img"]
+    assert n_img % world == 0, "image tokens must divide by the SP degree (jenga_hyvideo_multigpu.py:168-171)"
+    n_loc = n_img // world
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    q = torch.cat([full["q"][:, sl], full["q"][:, n_img:]], dim=1).contiguous()
+    k = torch.cat([full["k"][:, sl], full["k"][:, n_img:]], dim=1).contiguous()
+    v = torch.cat([full["v"][:, sl], full["v"][:, n_img:]], dim=1).contiguous()
+    # local cu_seqlens as get_cu_seqlens would build them from local shapes (attenion.py:34-57)
+    cu = torch.tensor([0, n_loc + wl["text_valid"], n_loc + wl["text_tokens"]], dtype=torch.int32, device=dev)
+    top_k = world * int((1 - wl["drop"]) * (n_loc // BLOCK))  # models_mul…:242,249-251
+    inp = dict(full)
+    del full
+    inp.update(q=None, k=None, v=None, top_k=top_k)
+    torch.cuda.empty_cache()
+    return dict(q=q, k=k, v=v, cu=cu, n_loc=n_loc, top_k=top_k, inp=inp, sp=UlyssesCarvedAttention(),
+                world=world, rank=rank)
+
+
+def bench_step(wl, st):
+    return my_parallel_attention(st["sp"], st["q"], st["k"], st["v"], st["n_loc"], st["n_loc"], st["cu"],
+                                 st["cu"], top_k=st["top_k"], text_amp=wl["text_amp"],
+                                 block_neighbor_list=st["inp"]["nbr"], p_remain_rates=wl["p_remain"])
+
+
+def bench_flops(wl, st, algorithmic_flops):
+    """Sum over ranks of the live tiles of each rank's head group."""
+    from .attention import block_sparse_attention_variant
+    captured = {}
+
+    def attn_fn(q, k, v, **kw):
+        kw.pop("shape_xfuse", None)
+        o, bits = block_sparse_attention_variant("hyvideo", q, k, v, kw.pop("top_k"), shape_xfuse=True,
+                                                 return_mask_bits=True, **kw)
+        captured["bits"] = bits
+        captured["heads"] = q.shape[2]
+        return o
+
+    sp = UlyssesCarvedAttention(attn_fn=attn_fn)
+    my_parallel_attention(sp, st["q"], st["k"], st["v"], st["n_loc"], st["n_loc"], st["cu"], st["cu"],
+                          top_k=st["top_k"], text_amp=wl["text_amp"], block_neighbor_list=st["inp"]["nbr"],
+                          p_remain_rates=wl["p_remain"])
+    inp = dict(st["inp"])
+    inp["heads"] = captured["heads"]
+    flops, pop = algorithmic_flops(wl, inp, captured["bits"])
+    t = torch.tensor([float(flops), float(pop)], dtype=torch.float64, device=st["q"].device)
+    dist.all_reduce(t)
+    return int(t[0].item()), int(t[1].item())
