@@ -10,12 +10,13 @@
 //   warps 2..5  softmax           one query row per thread: tcgen05.ld S -> online softmax in
 //                                 base 2 -> P as packed 16-bit back into TMEM; lazy O rescale;
 //                                 final O / l -> global
-// Two CTAs are co-resident per SM (256 TMEM columns and ~100 KB shared memory each) so one
-// CTA's softmax overlaps the other CTA's MMAs.
+// Key blocks are processed as two 64-key halves with S double-buffered in TMEM, so the tensor
+// pipe always runs one half ahead of the softmax warps (see the pipeline comment on the
+// kernel).  Two CTAs are co-resident per SM (256 TMEM columns and ~100 KB shared memory each).
 //
 // HBM/L2 layout: q,k,v stay in the caller's [B,S,H,D] layout; TMA boxes are {64 d, 128 rows}
-// with 128-byte swizzle, i.e. two 16 KB half tiles per 128x128 tile.  K half tiles are
-// K-major UMMA operands, V half tiles are MN-major UMMA operands (no transpose anywhere).
+// (Q: 128 rows) or {64 d, 64 rows} (K, V) with 128-byte swizzle.  K boxes are K-major UMMA
+// operands, V boxes are MN-major UMMA operands (no transpose anywhere).
 // CTAs are numbered head-major so that all CTAs in flight read the same head's K/V (59 MB at
 // 115K tokens) out of L2.
 #include "sm100_ptx.cuh"
@@ -26,22 +27,33 @@ namespace jenga {
 namespace {
 
 constexpr int kBlock = 128;           // rows per q block == keys per kv block
+constexpr int kHalf = 64;             // keys per half tile (the softmax / MMA pipelining unit)
 constexpr int kHeadDim = 128;
 constexpr int kThreads = 192;
-constexpr int kHalfTileBytes = kBlock * 64 * 2;  // 16 KB: 128 rows x 64 elems x 2 B
-constexpr int kTileBytes = 2 * kHalfTileBytes;   // 32 KB
+constexpr int kQHalfBytes = kBlock * 64 * 2;     // 16 KB: 128 q rows x 64 d
+constexpr int kQTileBytes = 2 * kQHalfBytes;     // 32 KB
+constexpr int kKVBoxBytes = kHalf * 64 * 2;      // 8 KB: 64 keys x 64 d  (one TMA box)
+constexpr int kKVSlotBytes = 2 * kKVBoxBytes;    // 16 KB: 64 keys x 128 d (two d-halves)
 constexpr int kMaxMaskWords = 256;               // up to 8192 key blocks (1M tokens)
-constexpr uint32_t kTmemCols = 256;              // S/P: [0,128)  O: [128,256)
+constexpr uint32_t kTmemCols = 256;              // S_a [0,64)  S_b [64,128)  O [128,256)
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kTileBytes;
-constexpr int kOffV = kOffK + kTileBytes;
-constexpr int kOffBars = kOffV + kTileBytes;  // 8 mbarriers + tmem slot
+constexpr int kOffK = kOffQ + kQTileBytes;        // K_a, K_b
+constexpr int kOffV = kOffK + 2 * kKVSlotBytes;   // V_a, V_b
+constexpr int kOffBars = kOffV + 2 * kKVSlotBytes;
 constexpr int kOffMask = kOffBars + 128;
 constexpr int kSmemBytes = 1024 /*align slack*/ + kOffMask + kMaxMaskWords * 4;
 
-enum BarId { Q_FULL = 0, Q_READY, K_FULL, K_EMPTY, V_FULL, S_FULL, P_FULL, PV_DONE, NUM_BARS };
+// mbarriers.  [h] = key half (a = keys 0..63, b = keys 64..127 of the current key block).
+enum BarId {
+  Q_FULL = 0, Q_READY,
+  K_FULL0, K_FULL1, K_EMPTY0, K_EMPTY1,
+  V_FULL0, V_FULL1, V_EMPTY0, V_EMPTY1,   // V_EMPTY[h] == "PV of half h retired"
+  S_FULL0, S_FULL1, P_FULL0, P_FULL1,
+  NUM_BARS
+};
+static_assert(NUM_BARS * 8 + 4 <= 128, "barrier block overflow");
 
 struct KernelParams {
   int heads;
@@ -81,6 +93,17 @@ struct BlockWalker {
   }
 };
 
+// Pipeline of one CTA (one 128-row q block), per live key block j and key half h:
+//
+//   TMA      K_h(j) -> smem   V_h(j) -> smem                      (4 single-buffered 16 KB slots)
+//   tensor   S_h = Q~ K_h^T (N=64)  ...  O += P_h V_h (K=64)        (in-order tcgen05 pipe)
+//   softmax  ld S_h -> max -> exp2 -> P_h (16-bit, over S_h) -> arrive
+//
+// S is double-buffered across the two halves, so while the softmax warps work on S_a(j) the
+// tensor pipe runs S_b(j) and the PV of the previous half; S_h(j+1) is issued right behind
+// PV_h(j) — the tcgen05 pipe executes MMAs in issue order, so it overwrites S_h only after
+// PV_h(j) has consumed P_h(j).  The softmax warps therefore never wait for the tensor pipe in
+// steady state, and two co-resident CTAs per SM keep both the MUFU and the tensor pipe fed.
 template <bool kBF16>
 __global__ void __launch_bounds__(kThreads, 2)
 carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
@@ -90,7 +113,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem + kOffQ;
-  uint8_t* sK = smem + kOffK;
+  uint8_t* sK = smem + kOffK;  // + h * kKVSlotBytes
   uint8_t* sV = smem + kOffV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
@@ -123,13 +146,11 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     if (skip_all) {
       bits = 0;
     } else if (dense) {
-      const int lo = w * 32;
-      const int rem = p.nb_kv - lo;
+      const int rem = p.nb_kv - w * 32;
       bits = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
     } else {
       bits = p.mask_bits[(static_cast<size_t>(bh) * p.nq_sparse + qb) * nwords + w];
-      // never walk past the key blocks that exist
-      const int rem = p.nb_kv - w * 32;
+      const int rem = p.nb_kv - w * 32;  // never walk past the key blocks that exist
       if (rem < 32) bits &= rem > 0 ? ((1u << rem) - 1u) : 0u;
     }
     s_mask[w] = bits;
@@ -139,14 +160,9 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    mbar_init(&bars[Q_FULL], 1);
-    mbar_init(&bars[Q_READY], 128);
-    mbar_init(&bars[K_FULL], 1);
-    mbar_init(&bars[K_EMPTY], 1);
-    mbar_init(&bars[V_FULL], 1);
-    mbar_init(&bars[S_FULL], 1);
-    mbar_init(&bars[P_FULL], 128);
-    mbar_init(&bars[PV_DONE], 1);
+#pragma unroll
+    for (int i = 0; i < NUM_BARS; ++i)
+      mbar_init(&bars[i], (i == Q_READY || i == P_FULL0 || i == P_FULL1) ? 128u : 1u);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -154,8 +170,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // fp32 S, later packed P in columns [0,64)
-  const uint32_t tmem_O = tmem_base + 128;  // fp32 O accumulator
+  const uint32_t tmem_O = tmem_base + 128;  // fp32 O accumulator; S_h at tmem_base + 64*h
 
   int n_tiles = 0;
   for (int w = 0; w < nwords; ++w) n_tiles += __popc(s_mask[w]);
@@ -163,62 +178,89 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0 && n_tiles > 0) {
-      mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
+      mbar_arrive_expect_tx(&bars[Q_FULL], kQTileBytes);
       tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, static_cast<int>(q_row0), h, b);
-      tma_load_4d(sQ + kHalfTileBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b);
+      tma_load_4d(sQ + kQHalfBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b);
       BlockWalker it(s_mask, nwords);
       int j = 0;
       for (int blk = it.next(); blk >= 0; blk = it.next(), ++j) {
-        const int row0 = blk * kBlock;
         const uint32_t par = (j & 1) ^ 1;
-        mbar_wait(&bars[K_EMPTY], par, p.err_flag);
-        mbar_arrive_expect_tx(&bars[K_FULL], kTileBytes);
-        tma_load_4d(sK, &tm_k, &bars[K_FULL], 0, row0, h, b);
-        tma_load_4d(sK + kHalfTileBytes, &tm_k, &bars[K_FULL], 64, row0, h, b);
-        mbar_wait(&bars[PV_DONE], par, p.err_flag);  // V slot free == PV of tile j-1 retired
-        mbar_arrive_expect_tx(&bars[V_FULL], kTileBytes);
-        tma_load_4d(sV, &tm_v, &bars[V_FULL], 0, row0, h, b);
-        tma_load_4d(sV + kHalfTileBytes, &tm_v, &bars[V_FULL], 64, row0, h, b);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row0 = blk * kBlock + hh * kHalf;
+          uint8_t* dst = sK + hh * kKVSlotBytes;
+          mbar_wait(&bars[K_EMPTY0 + hh], par, p.err_flag);
+          mbar_arrive_expect_tx(&bars[K_FULL0 + hh], kKVSlotBytes);
+          tma_load_4d(dst, &tm_k, &bars[K_FULL0 + hh], 0, row0, h, b);
+          tma_load_4d(dst + kKVBoxBytes, &tm_k, &bars[K_FULL0 + hh], 64, row0, h, b);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row0 = blk * kBlock + hh * kHalf;
+          uint8_t* dst = sV + hh * kKVSlotBytes;
+          mbar_wait(&bars[V_EMPTY0 + hh], par, p.err_flag);
+          mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVSlotBytes);
+          tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
+          tma_load_4d(dst + kKVBoxBytes, &tm_v, &bars[V_FULL0 + hh], 64, row0, h, b);
+        }
       }
     }
   } else if (warp == 1) {
     // =============================== tcgen05 issuer ===============================
     if (lane == 0 && n_tiles > 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, /*b_mn_major=*/false, 128, 128);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, /*b_mn_major=*/true, 128, 128);
-      // K-major SW128 operands (Q, K): 8-row groups are 1024 B apart; LBO unused (=16 B)
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, /*b_mn_major=*/false, 128, kHalf);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, /*b_mn_major=*/true, 128, kHeadDim);
+      // K-major SW128 operands: 8-row groups are 1024 B apart (SBO); LBO unused (=16 B).
+      // Q: 128 rows, d-halves 16 KB apart.  K_h: 64 rows, d-halves 8 KB apart.
       const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024, UMMA_LAYOUT_SW128);
-      const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 16, 1024, UMMA_LAYOUT_SW128);
-      // MN-major SW128 operand (V): 64-wide d chunks are one half tile (16 KB) apart (LBO),
-      // 8-key groups are 1024 B apart (SBO)
-      const uint64_t v_desc =
-          umma_smem_desc(smem_u32(sV), kHalfTileBytes, 1024, UMMA_LAYOUT_SW128);
-
-      mbar_wait(&bars[Q_READY], 0, p.err_flag);
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t par = j & 1;
-        mbar_wait(&bars[K_FULL], par, p.err_flag);
-        if (j > 0) mbar_wait(&bars[PV_DONE], par ^ 1, p.err_flag);  // S/P columns free again
-        tc_fence_after();
+      // MN-major SW128 operand V_h: 64-wide d chunks are one 8 KB box apart (LBO), 8-key
+      // groups are 1024 B apart (SBO).
+      auto issue_qk = [&](int hh) {
+        const uint64_t k_desc =
+            umma_smem_desc(smem_u32(sK + hh * kKVSlotBytes), 16, 1024, UMMA_LAYOUT_SW128);
 #pragma unroll
         for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-          // 16 d-elements = 32 B inside the 128-B swizzle row; second d-half is +16 KB
-          const uint64_t off = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kHalfTileBytes) >> 4);
-          umma_ss(tmem_S, q_desc + off, k_desc + off, idesc_qk, kk > 0 ? 1u : 0u);
+          const uint64_t qoff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kQHalfBytes) >> 4);
+          const uint64_t koff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kKVBoxBytes) >> 4);
+          umma_ss(tmem_base + hh * kHalf, q_desc + qoff, k_desc + koff, idesc_qk, kk > 0 ? 1u : 0u);
         }
-        umma_commit(&bars[K_EMPTY]);
-        umma_commit(&bars[S_FULL]);
-
-        mbar_wait(&bars[V_FULL], par, p.err_flag);
-        mbar_wait(&bars[P_FULL], par, p.err_flag);
-        tc_fence_after();
+        umma_commit(&bars[K_EMPTY0 + hh]);
+        umma_commit(&bars[S_FULL0 + hh]);
+      };
+      auto issue_pv = [&](int hh, bool first) {
+        const uint64_t v_desc =
+            umma_smem_desc(smem_u32(sV + hh * kKVSlotBytes), kKVBoxBytes, 1024, UMMA_LAYOUT_SW128);
 #pragma unroll
-        for (int kk = 0; kk < kBlock / 16; ++kk) {
-          // 16 keys = 16 rows x 128 B inside each V half tile; P advances 8 packed columns
+        for (int kk = 0; kk < kHalf / 16; ++kk) {
+          // 16 keys = 16 rows x 128 B inside each V box; P advances 8 packed columns
           const uint64_t off = static_cast<uint64_t>((kk * 16 * 128) >> 4);
-          umma_ts(tmem_O, tmem_S + kk * 8, v_desc + off, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_ts(tmem_O, tmem_base + hh * kHalf + kk * 8, v_desc + off, idesc_pv,
+                  (!first || kk > 0) ? 1u : 0u);
         }
-        umma_commit(&bars[PV_DONE]);
+        umma_commit(&bars[V_EMPTY0 + hh]);
+      };
+
+      mbar_wait(&bars[Q_READY], 0, p.err_flag);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        mbar_wait(&bars[K_FULL0 + hh], 0, p.err_flag);
+        tc_fence_after();
+        issue_qk(hh);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t par = j & 1;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&bars[V_FULL0 + hh], par, p.err_flag);
+          mbar_wait(&bars[P_FULL0 + hh], par, p.err_flag);
+          tc_fence_after();
+          issue_pv(hh, j == 0 && hh == 0);
+          if (j + 1 < n_tiles) {
+            mbar_wait(&bars[K_FULL0 + hh], par ^ 1, p.err_flag);
+            tc_fence_after();
+            issue_qk(hh);  // overwrites S_h / P_h(j) strictly after PV_h(j): in-order pipe
+          }
+        }
       }
     }
   } else {
@@ -241,7 +283,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
         // ref :87-88  q = (q * qk_scale).to(dtype) — elementwise, so swizzle-agnostic
         uint4* q4 = reinterpret_cast<uint4*>(sQ);
 #pragma unroll 4
-        for (int i = 0; i < kTileBytes / 16 / 128; ++i) {
+        for (int i = 0; i < kQTileBytes / 16 / 128; ++i) {
           uint4 v = q4[st + i * 128];
           uint32_t* e = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
@@ -258,80 +300,84 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
       BlockWalker it(s_mask, nwords);
       int j = 0;
       for (int blk = it.next(); blk >= 0; blk = it.next(), ++j) {
-        mbar_wait(&bars[S_FULL], j & 1, p.err_flag);
-        tc_fence_after();
-        float s[128];
-        {
-          uint32_t* su = reinterpret_cast<uint32_t*>(s);
-          tmem_ld32(tmem_S + lane_base + 0, su + 0);
-          tmem_ld32(tmem_S + lane_base + 32, su + 32);
-          tmem_ld32(tmem_S + lane_base + 64, su + 64);
-          tmem_ld32(tmem_S + lane_base + 96, su + 96);
-          tmem_ld_wait();
-        }
-        const long long col0 = static_cast<long long>(blk) * kBlock;
-        if (!dense && blk >= p.text_block_start && p.text_amp != 0.f) {
+        // ref :113-114 — text_amp is a constant added to every score of a text key block, in
+        // log2 units (sparse class only, where c == 1): fold it into the exponent offset.
+        const float amp = (!dense && blk >= p.text_block_start) ? p.text_amp : 0.f;
 #pragma unroll
-          for (int i = 0; i < 128; ++i) s[i] += p.text_amp;  // ref :113-114 (log2 units)
-        }
-        if (col0 + kBlock > kv_limit) {
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t tmem_S = tmem_base + hh * kHalf + lane_base;
+          mbar_wait(&bars[S_FULL0 + hh], j & 1, p.err_flag);
+          tc_fence_after();
+          float s[kHalf];
+          {
+            uint32_t* su = reinterpret_cast<uint32_t*>(s);
+            tmem_ld32(tmem_S, su);
+            tmem_ld32(tmem_S + 32, su + 32);
+            tmem_ld_wait();
+          }
+          const long long col0 = static_cast<long long>(blk) * kBlock + hh * kHalf;
+          if (col0 + kHalf > kv_limit) {  // rare: only the half tile that straddles seqlen
+            asm volatile("" ::: "memory");  // keep this a branch, not 64 predicated selects
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (col0 + i >= kv_limit) s[i] = -INFINITY;  // ref :117-118
-        }
-        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+            for (int i = 0; i < kHalf; ++i)
+              if (col0 + i >= kv_limit) s[i] = -INFINITY;  // ref :117-118
+          }
+          float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
-        for (int i = 4; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, s[i]);
-          mx1 = fmaxf(mx1, s[i + 1]);
-          mx2 = fmaxf(mx2, s[i + 2]);
-          mx3 = fmaxf(mx3, s[i + 3]);
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
-        const float m_cand = fmaxf(m_used, mx);
-        // Lazy rescale: the reference rescales acc by exp2(m_old - m_new) every tile
-        // (:121-132).  O/l is invariant to the reference point, so we only move it when the
-        // max grew by more than 2^8 — the final O/l is the same up to fp32 rounding.
-        const bool need = (m_cand - m_used) > 8.0f;  // false for NaN (-inf - -inf)
-        if (__any_sync(0xffffffffu, need)) {
-          if (j > 0) {
-            const float alpha = (m_cand == -INFINITY) ? 1.0f : fast_exp2(m_used - m_cand);
-            // PV of tile j-1 has retired: S_FULL(j) is committed after the issuer waited on it
+          for (int i = 4; i < kHalf; i += 4) {
+            mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+            mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+          }
+          const float mx = fmaf(fmaxf(mx0, mx1), c, amp);
+          const float m_cand = fmaxf(m_used, mx);
+          // Lazy rescale: the reference rescales acc by exp2(m_old - m_new) every tile
+          // (:121-132).  O/l is invariant to the reference point, so we only move it when the
+          // max grew by more than 2^8 — the final O/l is the same up to fp32 rounding.
+          const bool need = (m_cand - m_used) > 8.0f;  // false for NaN (-inf - -inf)
+          if (__any_sync(0xffffffffu, need)) {
+            if (j > 0 || hh > 0) {
+              // every PV issued so far must have retired before O is touched: the most recent
+              // one is PV_{1-hh} of tile (hh ? j : j-1)
+              if (hh == 0) mbar_wait(&bars[V_EMPTY1], (j - 1) & 1, p.err_flag);
+              else mbar_wait(&bars[V_EMPTY0], j & 1, p.err_flag);
+              tc_fence_after();
+              const float alpha = (m_cand == -INFINITY) ? 1.0f : fast_exp2(m_used - m_cand);
 #pragma unroll 1
-            for (int cc = 0; cc < 128; cc += 16) {
-              uint32_t o[16];
-              tmem_ld16(tmem_O + lane_base + cc, o);
-              tmem_ld_wait();
+              for (int cc = 0; cc < 128; cc += 16) {
+                uint32_t o[16];
+                tmem_ld16(tmem_O + lane_base + cc, o);
+                tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(tmem_O + lane_base + cc, o);
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st16(tmem_O + lane_base + cc, o);
+              }
+              tmem_st_wait();
+              l_sum *= alpha;
             }
-            tmem_st_wait();
-            l_sum *= alpha;
+            m_used = m_cand;
           }
-          m_used = m_cand;
-        }
-        const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
-        float sum0 = 0.f, sum1 = 0.f;
+          const float off = amp - ((m_used == -INFINITY) ? 0.f : m_used);
+          float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 128; cc += 32) {
-          uint32_t pk[16];
+          for (int cc = 0; cc < kHalf; cc += 32) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(s[cc + 2 * i], c, -m_safe));
-            const float p1 = fast_exp2(fmaf(s[cc + 2 * i + 1], c, -m_safe));
-            sum0 += p0;  // ref :131 — l accumulates the unrounded fp32 p
-            sum1 += p1;
-            pk[i] = pack2<kBF16>(p0, p1);  // ref :128 — P is cast to the input dtype for PV
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = fast_exp2(fmaf(s[cc + 2 * i], c, off));
+              const float p1 = fast_exp2(fmaf(s[cc + 2 * i + 1], c, off));
+              sum0 += p0;  // ref :131 — l accumulates the unrounded fp32 p
+              sum1 += p1;
+              pk[i] = pack2<kBF16>(p0, p1);  // ref :128 — P is cast to the input dtype for PV
+            }
+            tmem_st16(tmem_S + (cc >> 1), pk);
           }
-          tmem_st16(tmem_S + lane_base + (cc >> 1), pk);
+          l_sum += sum0 + sum1;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars[P_FULL0 + hh]);
         }
-        l_sum += sum0 + sum1;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars[P_FULL]);
       }
-      mbar_wait(&bars[PV_DONE], (n_tiles - 1) & 1, p.err_flag);
+      mbar_wait(&bars[V_EMPTY1], (n_tiles - 1) & 1, p.err_flag);  // last PV retired (in-order)
       tc_fence_after();
     }
 
@@ -367,12 +413,11 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
           if (!p.out_f32) {
             *reinterpret_cast<uint4*>(orow + cc + i) = v;
           } else {  // wan/…:530-532: the 16-bit result is widened back to the query dtype
-            float4 f0, f1;
             float2 t0 = unpack2<kBF16>(e[0]), t1 = unpack2<kBF16>(e[1]);
-            f0 = make_float4(t0.x, t0.y, t1.x, t1.y);
+            const float4 f0 = make_float4(t0.x, t0.y, t1.x, t1.y);
             t0 = unpack2<kBF16>(e[2]);
             t1 = unpack2<kBF16>(e[3]);
-            f1 = make_float4(t0.x, t0.y, t1.x, t1.y);
+            const float4 f1 = make_float4(t0.x, t0.y, t1.x, t1.y);
             *reinterpret_cast<float4*>(orow32 + cc + i) = f0;
             *reinterpret_cast<float4*>(orow32 + cc + i + 4) = f1;
           }
@@ -393,14 +438,15 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
 // Host side
 // ------------------------------------------------------------------------------------------
 static int make_tile_map(CUtensorMap* map, const void* base, int dtype, long long rows, int heads,
-                         int batch, long long stride_b, long long stride_s, long long stride_h) {
-  // dims (fastest first): d, row, head, batch.  Box {64, 128, 1, 1}, 128-B swizzle.
+                         int batch, long long stride_b, long long stride_s, long long stride_h,
+                         int box_rows) {
+  // dims (fastest first): d, row, head, batch.  Box {64, box_rows, 1, 1}, 128-B swizzle.
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(rows),
                               static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(batch)};
   const cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride_s) * 2,
                                  static_cast<cuuint64_t>(stride_h) * 2,
                                  static_cast<cuuint64_t>(stride_b) * 2};
-  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(kBlock), 1, 1};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
   const cuuint32_t elem_strides[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt =
       dtype == JENGA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -446,13 +492,13 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;
   if ((rc = make_tile_map(&tm_q, a->q, a->dtype, a->q_rows, a->heads, a->batch, a->q_stride_b,
-                          a->q_stride_s, a->q_stride_h)))
+                          a->q_stride_s, a->q_stride_h, kBlock)))
     return rc;
   if ((rc = make_tile_map(&tm_k, a->k, a->dtype, a->kv_rows, a->heads, a->batch, a->k_stride_b,
-                          a->k_stride_s, a->k_stride_h)))
+                          a->k_stride_s, a->k_stride_h, kHalf)))
     return rc;
   if ((rc = make_tile_map(&tm_v, a->v, a->dtype, a->kv_rows, a->heads, a->batch, a->v_stride_b,
-                          a->v_stride_s, a->v_stride_h)))
+                          a->v_stride_s, a->v_stride_h, kHalf)))
     return rc;
 
   KernelParams p{};

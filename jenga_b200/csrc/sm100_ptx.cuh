@@ -70,9 +70,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > (1ll << 31)) {
+  for (;;) {
+    // tight inner loop: try_wait suspends the thread in hardware until the phase flips or a
+    // time limit passes, so 256 probes are cheap in issue slots
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if ((clock64() - t0) > (1ll << 31)) {
       if (err_flag) atomicExch(err_flag, JENGA_DEV_WATCHDOG);
       __threadfence_system();
       __trap();

@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -25 | tee gpurun_out/gpu_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log
-# launch list of one bench step (cold-cache, serialised: shares only)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-# full capture of the attention kernel (3 launches)
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:carved_attn -s 1 -c 2 -o gpurun_out/attn_full -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu2.log 2>&1
-ls -la gpurun_out
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | tail -3 | tee gpurun_out/bench_v2.log
