@@ -8,8 +8,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "_C" / "libjenga_b200.so"
+# JENGA_B200_LIB selects a tuning variant built by `python -m jenga_b200.build --variant ...`
+LIB_PATH = Path(os.environ.get("JENGA_B200_LIB") or (_PKG / "_C" / "libjenga_b200.so"))
 
 JENGA_BF16, JENGA_F16, JENGA_F32 = 0, 1, 2
 

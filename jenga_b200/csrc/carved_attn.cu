@@ -22,6 +22,13 @@
 #include "sm100_ptx.cuh"
 #include "jenga_internal.h"
 
+#ifndef JENGA_POLY_EVERY
+#define JENGA_POLY_EVERY 3
+#endif
+#ifndef JENGA_QK_FULL
+#define JENGA_QK_FULL 0
+#endif
+
 namespace jenga {
 
 namespace {
@@ -36,6 +43,8 @@ constexpr int kKVBoxBytes = kHalf * 64 * 2;      // 8 KB: 64 keys x 64 d  (one T
 constexpr int kKVSlotBytes = 2 * kKVBoxBytes;    // 16 KB: 64 keys x 128 d (two d-halves)
 constexpr int kMaxMaskWords = 256;               // up to 8192 key blocks (1M tokens)
 constexpr uint32_t kTmemCols = 256;              // S_a [0,64)  S_b [64,128)  O [128,256)
+constexpr bool kQKFull = JENGA_QK_FULL != 0;      // 1: one N=128 QK issue per tile (A read once per k-step)
+constexpr int kPolyEvery = JENGA_POLY_EVERY;     // every n-th exp2 pair uses the FMA-pipe polynomial (0 = never)
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 constexpr int kOffQ = 0;
@@ -187,12 +196,14 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
         const uint32_t par = (j & 1) ^ 1;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+          // K boxes are laid out [d half][key half] (4 x 8 KB) so that the 128 keys of one d
+          // half are contiguous: serves two N=64 operands or one N=128 operand.
           const int row0 = blk * kBlock + hh * kHalf;
-          uint8_t* dst = sK + hh * kKVSlotBytes;
+          uint8_t* dst = sK + hh * kKVBoxBytes;
           mbar_wait(&bars[K_EMPTY0 + hh], par, p.err_flag);
           mbar_arrive_expect_tx(&bars[K_FULL0 + hh], kKVSlotBytes);
           tma_load_4d(dst, &tm_k, &bars[K_FULL0 + hh], 0, row0, h, b);
-          tma_load_4d(dst + kKVBoxBytes, &tm_k, &bars[K_FULL0 + hh], 64, row0, h, b);
+          tma_load_4d(dst + 2 * kKVBoxBytes, &tm_k, &bars[K_FULL0 + hh], 64, row0, h, b);
         }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -217,15 +228,30 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
       // groups are 1024 B apart (SBO).
       auto issue_qk = [&](int hh) {
         const uint64_t k_desc =
-            umma_smem_desc(smem_u32(sK + hh * kKVSlotBytes), 16, 1024, UMMA_LAYOUT_SW128);
+            umma_smem_desc(smem_u32(sK + hh * kKVBoxBytes), 16, 1024, UMMA_LAYOUT_SW128);
 #pragma unroll
         for (int kk = 0; kk < kHeadDim / 16; ++kk) {
           const uint64_t qoff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kQHalfBytes) >> 4);
-          const uint64_t koff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kKVBoxBytes) >> 4);
+          const uint64_t koff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * 2 * kKVBoxBytes) >> 4);
           umma_ss(tmem_base + hh * kHalf, q_desc + qoff, k_desc + koff, idesc_qk, kk > 0 ? 1u : 0u);
         }
         umma_commit(&bars[K_EMPTY0 + hh]);
         umma_commit(&bars[S_FULL0 + hh]);
+      };
+      // One N=128 issue for the whole key block: Q (the A operand, 4 KB per k-step) is read
+      // from shared memory once instead of once per half.
+      auto issue_qk_full = [&]() {
+        constexpr uint32_t idesc_full = umma_idesc_f16(kBF16, false, 128, kBlock);
+        const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 16, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+          const uint64_t off = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kQHalfBytes) >> 4);
+          umma_ss(tmem_base, q_desc + off, k_desc + off, idesc_full, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&bars[K_EMPTY0]);
+        umma_commit(&bars[K_EMPTY1]);
+        umma_commit(&bars[S_FULL0]);
+        umma_commit(&bars[S_FULL1]);
       };
       auto issue_pv = [&](int hh, bool first) {
         const uint64_t v_desc =
@@ -241,11 +267,18 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
       };
 
       mbar_wait(&bars[Q_READY], 0, p.err_flag);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        mbar_wait(&bars[K_FULL0 + hh], 0, p.err_flag);
+      if constexpr (kQKFull) {
+        mbar_wait(&bars[K_FULL0], 0, p.err_flag);
+        mbar_wait(&bars[K_FULL1], 0, p.err_flag);
         tc_fence_after();
-        issue_qk(hh);
+        issue_qk_full();
+      } else {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&bars[K_FULL0 + hh], 0, p.err_flag);
+          tc_fence_after();
+          issue_qk(hh);
+        }
       }
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t par = j & 1;
@@ -256,9 +289,18 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
           tc_fence_after();
           issue_pv(hh, j == 0 && hh == 0);
           if (j + 1 < n_tiles) {
-            mbar_wait(&bars[K_FULL0 + hh], par ^ 1, p.err_flag);
-            tc_fence_after();
-            issue_qk(hh);  // overwrites S_h / P_h(j) strictly after PV_h(j): in-order pipe
+            if constexpr (kQKFull) {
+              if (hh == 1) {
+                mbar_wait(&bars[K_FULL0], par ^ 1, p.err_flag);
+                mbar_wait(&bars[K_FULL1], par ^ 1, p.err_flag);
+                tc_fence_after();
+                issue_qk_full();
+              }
+            } else {
+              mbar_wait(&bars[K_FULL0 + hh], par ^ 1, p.err_flag);
+              tc_fence_after();
+              issue_qk(hh);  // overwrites S_h / P_h(j) strictly after PV_h(j): in-order pipe
+            }
           }
         }
       }
@@ -357,20 +399,36 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
             m_used = m_cand;
           }
           const float off = amp - ((m_used == -INFINITY) ? 0.f : m_used);
-          float sum0 = 0.f, sum1 = 0.f;
+          // p = exp2(s*c + off) on packed pairs.  Every third pair takes the polynomial path
+          // (FMA/ALU pipes) so the MUFU — 16 ex2/clk/SM, as long as the tile's MMAs — is not
+          // the co-bottleneck; l accumulates the unrounded p (ref :131), P is rounded to the
+          // input dtype for the PV product (ref :128).
+          const f32x2 c2 = f2_pack(c, c), off2 = f2_pack(off, off);
+          f32x2 sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
           for (int cc = 0; cc < kHalf; cc += 32) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = fast_exp2(fmaf(s[cc + 2 * i], c, off));
-              const float p1 = fast_exp2(fmaf(s[cc + 2 * i + 1], c, off));
-              sum0 += p0;  // ref :131 — l accumulates the unrounded fp32 p
-              sum1 += p1;
-              pk[i] = pack2<kBF16>(p0, p1);  // ref :128 — P is cast to the input dtype for PV
+              const f32x2 x = f2_fma(f2_pack(s[cc + 2 * i], s[cc + 2 * i + 1]), c2, off2);
+              float x0, x1, p0, p1;
+              f2_unpack(x, x0, x1);
+              f32x2 pp;
+              if (kPolyEvery > 0 && (i % kPolyEvery) == kPolyEvery - 1) {
+                pp = f2_exp2_poly(f2_pack(fmaxf(x0, -125.f), fmaxf(x1, -125.f)));
+                f2_unpack(pp, p0, p1);
+              } else {
+                p0 = fast_exp2(x0);
+                p1 = fast_exp2(x1);
+                pp = f2_pack(p0, p1);
+              }
+              sum2 = f2_add(sum2, pp);
+              pk[i] = pack2<kBF16>(p0, p1);
             }
             tmem_st16(tmem_S + (cc >> 1), pk);
           }
+          float sum0, sum1;
+          f2_unpack(sum2, sum0, sum1);
           l_sum += sum0 + sum1;
           tmem_st_wait();
           tc_fence_before();

@@ -263,6 +263,52 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, two lanes per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split x = n + f with
+// f in [-0.5, 0.5] (magic-number rounding), degree-3 minimax polynomial for 2^f (max relative
+// error 7.5e-5, i.e. ~1/25 of a bf16 ulp), exponent patched in with an integer shift-add.
+// x must be >= -125 (callers clamp) and < 128.
+__device__ __forceinline__ f32x2 f2_exp2_poly(f32x2 x) {
+  const f32x2 magic = f2_pack(12582912.0f, 12582912.0f);      // 1.5 * 2^23
+  const f32x2 nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const f32x2 neg1 = f2_pack(-1.0f, -1.0f);
+  const f32x2 c0 = f2_pack(0.9999280571937561f, 0.9999280571937561f);
+  const f32x2 c1 = f2_pack(0.6932609677314758f, 0.6932609677314758f);
+  const f32x2 c2 = f2_pack(0.2426111251115799f, 0.2426111251115799f);
+  const f32x2 c3 = f2_pack(0.0551716648042202f, 0.0551716648042202f);
+  const f32x2 t = f2_add(x, magic);          // low mantissa bits of t = round(x)
+  const f32x2 n = f2_add(t, nmagic);         // round(x) as a float
+  const f32x2 f = f2_fma(n, neg1, x);        // x - round(x)
+  f32x2 pz = f2_fma(c3, f, c2);
+  pz = f2_fma(pz, f, c1);
+  pz = f2_fma(pz, f, c0);
+  float plo, phi, tlo, thi;
+  f2_unpack(pz, plo, phi);
+  f2_unpack(t, tlo, thi);
+  const float rlo = __uint_as_float(__float_as_uint(plo) + (__float_as_uint(tlo) << 23));
+  const float rhi = __uint_as_float(__float_as_uint(phi) + (__float_as_uint(thi) << 23));
+  return f2_pack(rlo, rhi);
+}
+
 // {hi, lo} fp32 -> packed 16-bit pair, round-to-nearest-even (lo lands in bits [0,16)).
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
