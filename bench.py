@@ -247,6 +247,10 @@ def main():
     ap.add_argument("--workload", default="hy720p")
     ap.add_argument("--drop", type=float, default=0.7)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dit-loop", type=int, default=0, metavar="STEPS",
+                    help="also run the step-skip schedule harness for this many computed steps "
+                         "(23 = the whole 50-step video: 1380 hot-path calls) and report measured "
+                         "hot-path seconds per video")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -360,6 +364,7 @@ def main():
                 traffic = None
         roof = {"bound": "tensor", "kernel": "carved_attn_fwd_kernel", "achieved": ach, "peak": pk["bf16_burst"],
                 "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"], "traffic": traffic, "ms_per_launch": ams,
+                "frac_of_sustained_peak": ach / pk["bf16_sustained"], "sustained_peak": pk["bf16_sustained"],
                 "peak_source": pk["source"] + ", bf16 burst (kernel timed alone)",
                 "algorithmic_flops_per_launch": flops, "live_tiles": pop}
 
@@ -391,6 +396,34 @@ def main():
                "d2h_bytes_per_step": hout.numel() * hout.element_size()}
         del hq, hk, hv, dq, dk, dv, hout
 
+    dit = None
+    if args.dit_loop > 0 and world == 1 and wl["variant"] == "hyvideo":
+        from jenga_b200 import dit_loop
+        L, T, H = inp["n_img"], wl["text_tokens"], inp["heads"]
+        g = torch.Generator(device=dev).manual_seed(77)
+        img_qkv = torch.empty(1, L, 3 * H * 128, dtype=torch.bfloat16, device=dev)
+        # q,k parts: the model-like synthetic tokens (pre-norm scale 1.5), v part: N(0,1)
+        img_qkv.view(1, L, 3, H, 128)[:, :, 0] = inp["q"][:, :L] * 1.5
+        img_qkv.view(1, L, 3, H, 128)[:, :, 1] = inp["k"][:, :L] * 1.5
+        img_qkv.view(1, L, 3, H, 128)[:, :, 2] = inp["v"][:, :L]
+        txt_qkv = torch.randn(1, T, 3 * H * 128, generator=g, device=dev).to(torch.bfloat16)
+        ws = [torch.ones(128, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+        ang = torch.rand(L, 64, generator=g, device=dev) * 6.2831853
+        cos = torch.cos(ang).repeat_interleave(2, dim=1).contiguous()
+        sin = torch.sin(ang).repeat_interleave(2, dim=1).contiguous()
+        dit_loop.run_hot_path_loop(img_qkv, txt_qkv, H, ws, (cos, sin), inp["nbr"], inp["cu"],
+                                   p_remain=wl["p_remain"], max_computed_steps=1)  # warm-up: 60 calls
+        sec, calls = dit_loop.run_hot_path_loop(img_qkv, txt_qkv, H, ws, (cos, sin), inp["nbr"], inp["cu"],
+                                                p_remain=wl["p_remain"], sa_drop_rates=(args.drop, min(args.drop + 0.1, 0.95)),
+                                                max_computed_steps=args.dit_loop)
+        n_sched = sum(1 for s_ in dit_loop.schedule() if s_[1])
+        dit = {"computed_steps_run": args.dit_loop, "computed_steps_per_video": n_sched, "calls": calls,
+               "seconds": sec, "hot_path_sec_per_video": sec * n_sched / args.dit_loop,
+               "ms_per_call": 1e3 * sec / calls,
+               "includes": "attention_prologue (RMSNorm+RoPE+cat+pool) + select_blocks + carved attention; "
+                           "DiT dense layers out of scope"}
+        del img_qkv, txt_qkv
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         tf, sample, _, ncores = cpu_sample(wl, "port")
@@ -418,6 +451,8 @@ def main():
             line["roofline"] = roof
         if cpu:
             line["cpu_baseline"] = cpu
+        if dit:
+            line["dit_loop"] = dit
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -205,6 +205,32 @@ typedef struct JengaHyPrologueArgs {
 
 int jenga_hy_prologue(const JengaHyPrologueArgs* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (a-5, a-6, Wan variant) WanRMSNorm over the full channel dim + 3-axis complex RoPE.
+ * ref: wan/modules/model_mul.py:74-90 (WanRMSNorm), :40-71 (rope_apply incl. freq_remap),
+ *      :145-151 (qkv_fn).  x: [B, L, H*128] projection output (bf16 or f32, element strides);
+ * w: [H*128] norm weight (bf16 or f32; NULL = ones).  freqs: the reference's complex128 table
+ * viewed as doubles [freq_rows, 64, 2]; grid = (F, H, W) latent grid; freq_remap (optional int64
+ * [F*H*W]) = hilbert_order.  out: [B, L, H, 128] bf16 = bf16(float(fp64 rotation)), i.e. what
+ * block_sparse_attention sees after its own cast (wan/...triton_diffres.py:456-463).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct JengaWanPrologueArgs {
+  const void* x;
+  const void* w;
+  int32_t x_dtype, w_dtype;
+  int32_t batch, heads, head_dim;
+  int64_t tokens;
+  int64_t stride_b, stride_s;
+  float eps;
+  const double* freqs;
+  int32_t freq_rows;
+  int32_t grid_f, grid_h, grid_w;
+  const int64_t* freq_remap;
+  void* out;
+} JengaWanPrologueArgs;
+
+int jenga_wan_prologue(const JengaWanPrologueArgs* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,17 @@ class JengaHyPrologueArgs(C.Structure):
     ]
 
 
+class JengaWanPrologueArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("x_dtype", C.c_int32), ("w_dtype", C.c_int32),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("tokens", C.c_int64),
+        ("stride_b", C.c_int64), ("stride_s", C.c_int64), ("eps", C.c_float),
+        ("freqs", C.c_void_p), ("freq_rows", C.c_int32),
+        ("grid_f", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32),
+        ("freq_remap", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
 def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise JengaError(
@@ -99,6 +110,8 @@ def _load() -> C.CDLL:
     lib.jenga_select_blocks.restype = C.c_int
     lib.jenga_hy_prologue.argtypes = [C.POINTER(JengaHyPrologueArgs), C.c_void_p]
     lib.jenga_hy_prologue.restype = C.c_int
+    lib.jenga_wan_prologue.argtypes = [C.POINTER(JengaWanPrologueArgs), C.c_void_p]
+    lib.jenga_wan_prologue.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 1:

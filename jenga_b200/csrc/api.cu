@@ -156,3 +156,7 @@ extern "C" int jenga_select_blocks(const JengaSelectArgs* args, void* stream) {
 extern "C" int jenga_hy_prologue(const JengaHyPrologueArgs* args, void* stream) {
   return hy_prologue_impl(args, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int jenga_wan_prologue(const JengaWanPrologueArgs* args, void* stream) {
+  return wan_prologue_impl(args, static_cast<cudaStream_t>(stream));
+}

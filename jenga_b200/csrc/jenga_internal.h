@@ -25,5 +25,6 @@ int block_pool_impl(const void* x, void* pooled, void* cast_out, int in_dtype, i
                     long long sh, int n_blocks, cudaStream_t stream);
 int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream);
 int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream);
+int wan_prologue_impl(const JengaWanPrologueArgs* a, cudaStream_t stream);
 
 }  // namespace jenga

@@ -251,3 +251,121 @@ int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream) {
 }
 
 }  // namespace jenga
+
+// =============================================================================================
+// Wan2.1 self-attention prologue: full-width RMSNorm (WanRMSNorm, wan/modules/model_mul.py:74-90)
+// + 3-axis complex RoPE in fp64 (rope_apply :40-71, with the freq_remap gather :63-65), output
+// rounded fp64 -> fp32 (`.float()` :71) -> bf16 (the operator's cast, wan/...diffres.py:456-463).
+// One warp per token; two passes over the token's C = H*D channels (second pass hits L1/L2).
+// =============================================================================================
+namespace jenga {
+namespace {
+
+struct WanPrologueParams {
+  const void* x;        // [B, L, C] projection output (bf16 or f32)
+  const void* w;        // [C] norm weight (bf16 or f32)
+  int x_f32, w_f32;
+  long long sb, ss;     // element strides of x (batch, token)
+  int L, C, H;          // tokens, channels, heads (D = C / H = 128)
+  float eps;
+  const double* freqs;  // [rows, 64, 2] (re, im) — torch.view_as_real of the complex128 table
+  int freq_rows;
+  int gf, gh, gw;       // latent grid (F, H, W); tokens >= F*H*W get no rotation (:66)
+  const long long* remap;  // optional [F*H*W]: position of token i (hilbert_order)
+  uint16_t* out;        // [B, L, H, 128] bf16, contiguous
+};
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void __launch_bounds__(256)
+wan_prologue_kernel(const WanPrologueParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= p.L) return;
+  const long long tok = warp;
+  const char* xrow = static_cast<const char*>(p.x) + (b * p.sb + tok * p.ss) * (p.x_f32 ? 4 : 2);
+  auto load_x = [&](int c) -> float {
+    return p.x_f32 ? reinterpret_cast<const float*>(xrow)[c]
+                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(xrow)[c]);
+  };
+  // pass 1: mean of squares in fp32 (x.float().pow(2).mean(-1))
+  float ss = 0.f;
+  for (int c = lane * 2; c < p.C; c += 64) {
+    const float a = load_x(c), bb = load_x(c + 1);
+    ss = fmaf(a, a, ss);
+    ss = fmaf(bb, bb, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = rsqrtf(ss / static_cast<float>(p.C) + p.eps);
+  // rotation source position
+  const long long n_grid = static_cast<long long>(p.gf) * p.gh * p.gw;
+  const bool rotate = tok < n_grid && p.freqs != nullptr;
+  int fi = 0, hi = 0, wi = 0;
+  if (rotate) {
+    const long long pos = p.remap ? __ldg(p.remap + tok) : tok;
+    fi = static_cast<int>(pos / (static_cast<long long>(p.gh) * p.gw));
+    const int rem = static_cast<int>(pos - static_cast<long long>(fi) * p.gh * p.gw);
+    hi = rem / p.gw;
+    wi = rem - hi * p.gw;
+  }
+  const int c3 = 64 / 3;              // 21
+  const int s0 = 64 - 2 * c3;         // 22: split sizes [22, 21, 21] (:44)
+  // pass 2: one complex pair (2 channels) per lane step
+  for (int c = lane * 2; c < p.C; c += 64) {
+    float y[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float v = __fmul_rn(load_x(c + t), r);          // _norm in fp32
+      if (!p.x_f32) v = bf16_round(v);                // .type_as(x)
+      float wv = p.w ? (p.w_f32 ? reinterpret_cast<const float*>(p.w)[c + t]
+                                : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.w)[c + t]))
+                     : 1.0f;
+      v = __fmul_rn(v, wv);                            // * self.weight (promotes to fp32 unless both bf16)
+      if (!p.x_f32 && !p.w_f32) v = bf16_round(v);
+      y[t] = v;
+    }
+    float o0 = y[0], o1 = y[1];
+    if (rotate) {
+      const int j = (c & 127) >> 1;  // complex index inside the head
+      const int row = j < s0 ? fi : (j < s0 + c3 ? hi : wi);
+      const double2 f = __ldg(reinterpret_cast<const double2*>(p.freqs) + static_cast<long long>(row) * 64 + j);
+      const double a = static_cast<double>(y[0]), bb = static_cast<double>(y[1]);
+      // complex128 product (a + bi)(c + di), then .float()
+      o0 = static_cast<float>(a * f.x - bb * f.y);
+      o1 = static_cast<float>(a * f.y + bb * f.x);
+    }
+    const uint32_t packed = pack2<true>(o0, o1);
+    reinterpret_cast<uint32_t*>(p.out + (static_cast<long long>(b) * p.L + tok) * p.C)[c >> 1] = packed;
+  }
+}
+
+}  // namespace
+
+int wan_prologue_impl(const JengaWanPrologueArgs* a, cudaStream_t stream) {
+  if (!a || !a->x || !a->out) return set_error(JENGA_E_INVALID, "wan_prologue: null pointer");
+  if (a->head_dim != 128) return set_error(JENGA_E_UNSUPPORTED, "wan_prologue: head_dim must be 128");
+  if (a->batch <= 0 || a->tokens <= 0 || a->heads <= 0) return set_error(JENGA_E_INVALID, "wan_prologue: bad shape");
+  if ((a->x_dtype != JENGA_BF16 && a->x_dtype != JENGA_F32) || (a->w && a->w_dtype != JENGA_BF16 && a->w_dtype != JENGA_F32))
+    return set_error(JENGA_E_INVALID, "wan_prologue: dtypes must be bf16 or f32");
+  if (a->freqs && (a->grid_f <= 0 || a->grid_h <= 0 || a->grid_w <= 0 || a->grid_f > a->freq_rows ||
+                   a->grid_h > a->freq_rows || a->grid_w > a->freq_rows))
+    return set_error(JENGA_E_INVALID, "wan_prologue: grid exceeds the frequency table");
+  WanPrologueParams p{};
+  p.x = a->x; p.w = a->w;
+  p.x_f32 = a->x_dtype == JENGA_F32; p.w_f32 = a->w_dtype == JENGA_F32;
+  p.sb = a->stride_b; p.ss = a->stride_s;
+  p.L = static_cast<int>(a->tokens); p.H = a->heads; p.C = a->heads * 128;
+  p.eps = a->eps;
+  p.freqs = a->freqs; p.freq_rows = a->freq_rows;
+  p.gf = a->grid_f; p.gh = a->grid_h; p.gw = a->grid_w;
+  p.remap = reinterpret_cast<const long long*>(a->freq_remap);
+  p.out = static_cast<uint16_t*>(a->out);
+  dim3 grid(static_cast<unsigned>((a->tokens + 7) / 8), static_cast<unsigned>(a->batch));
+  wan_prologue_kernel<<<grid, 256, 0, stream>>>(p);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "wan_prologue launch");
+}
+
+}  // namespace jenga

@@ -150,18 +150,21 @@ struct SelectParams {
 };
 
 // Warp-cooperative bitonic sort, descending, of n2 (power of two) 64-bit keys in shared memory.
+// Each lane owns n2/64 compare-exchange PAIRS per pass (no idle half), indexed so that the two
+// elements of a pair are (i, i|j) with bit j of i clear.
 __device__ void warp_bitonic_desc(unsigned long long* keys, int n2, int lane) {
+  const int npairs = n2 >> 1;
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < n2; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          const bool desc_seg = (i & k) == 0;
-          if (desc_seg ? (a < b) : (a > b)) {
-            keys[i] = b;
-            keys[ixj] = a;
-          }
+#pragma unroll 4
+      for (int t = lane; t < npairs; t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i | j;
+        const unsigned long long a = keys[i], b = keys[ixj];
+        const bool desc_seg = (i & k) == 0;
+        if (desc_seg ? (a < b) : (a > b)) {
+          keys[i] = b;
+          keys[ixj] = a;
         }
       }
       __syncwarp();

@@ -201,8 +201,51 @@ def prologue_goldens():
     print("prologue", q.shape, float(q.float().abs().mean()), flush=True)
 
 
+def wan_prologue_goldens():
+    """WanRMSNorm + rope_apply (wan/modules/model_mul.py:74-90, :40-71, :145-151) from the
+    reference file itself.  model_mul.py imports diffusers mixins and its sibling modules at
+    import time; they are stubbed / resolved through a synthetic `wan.modules` package so that
+    wan/__init__.py (which pulls the whole pipeline) is not executed."""
+    import synth
+    for name, attrs in (("diffusers", {}), ("diffusers.configuration_utils",
+                                            {"ConfigMixin": object, "register_to_config": lambda f: f}),
+                        ("diffusers.models", {}), ("diffusers.models.modeling_utils", {"ModelMixin": torch.nn.Module})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules.setdefault(name, m)
+    for name, path in (("wan", REF / "wan"), ("wan.modules", REF / "wan" / "modules")):
+        m = types.ModuleType(name)
+        m.__path__ = [str(path)]
+        sys.modules[name] = m
+    import importlib
+    mm = importlib.import_module("wan.modules.model_mul")
+    c = synth.wan_prologue_case()
+    H, (f, h, w) = c["H"], c["grid"]
+    d = 128
+    freqs = torch.cat([mm.rope_params(1024, d - 4 * (d // 6)), mm.rope_params(1024, 2 * (d // 6)),
+                       mm.rope_params(1024, 2 * (d // 6))], dim=1)        # wan/modules/model_mul.py (WanModel.__init__)
+    grid_sizes = torch.tensor([[f, h, w]])
+    out = {}
+    for tag, x, wt in (("q", c["xq"], c["wq"]), ("k", c["xk"], c["wk"])):
+        norm = mm.WanRMSNorm(H * d, eps=1e-6)
+        with torch.no_grad():
+            norm.weight.copy_(wt)
+            y = norm(x).view(1, c["L"], H, d)
+            r = mm.rope_apply(y, grid_sizes, freqs, c["remap"])
+        assert r.dtype == torch.float32
+        out[tag] = r.to(torch.bfloat16).view(torch.int16).numpy()   # the operator's cast (…diffres.py:456-463)
+    out["freqs_sha"] = np.frombuffer(sha16(torch.view_as_real(freqs).numpy()).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT / "wan_prologue.npz", **out)
+    for name in ("wan", "wan.modules", "wan.modules.model_mul", "wan.modules.attention",
+                 "wan.modules.attention_block_triton_diffres"):
+        sys.modules.pop(name, None)
+    print("wan_prologue", out["q"].shape, flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gilbert", "attention", "mask", "prologue"]
+    which = sys.argv[1:] or ["gilbert", "attention", "mask", "prologue", "wan_prologue"]
+    if "wan_prologue" in which:
+        wan_prologue_goldens()
     if "prologue" in which:
         prologue_goldens()
     if "gilbert" in which:

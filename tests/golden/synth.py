@@ -130,3 +130,22 @@ def prologue_case():
     ws = [(1.0 + 0.2 * normal((128,), c["seed"] + 2 + i)).bfloat16() for i in range(4)]
     return dict(L=L, T=T, H=H, grid=c["grid"], img=img, txt=txt, w_img_q=ws[0], w_img_k=ws[1],
                 w_txt_q=ws[2], w_txt_k=ws[3])
+
+
+WAN_PROLOGUE_CASE = dict(grid=(3, 4, 6), pad=8, H=2, seed=61)  # 72 grid tokens + 8 padding tokens
+
+
+def wan_prologue_case():
+    """q/k projection outputs [1, L, H*128] bf16, fp32 norm weights [H*128]."""
+    c = WAN_PROLOGUE_CASE
+    f, h, w = c["grid"]
+    L = f * h * w + c["pad"]
+    C = c["H"] * 128
+    xq = (1.3 * normal((1, L, C), c["seed"])).bfloat16()
+    xk = (0.9 * normal((1, L, C), c["seed"] + 1)).bfloat16()
+    wq = 1.0 + 0.2 * normal((C,), c["seed"] + 2)
+    wk = 1.0 + 0.2 * normal((C,), c["seed"] + 3)
+    n = f * h * w
+    # a fixed pseudo-random permutation standing in for hilbert_order
+    remap = torch.from_numpy(np.argsort(_splitmix64(np.arange(n, dtype=np.uint64) + np.uint64(99)), kind="stable").astype(np.int64))
+    return dict(L=L, H=c["H"], grid=c["grid"], xq=xq, xk=xk, wq=wq, wk=wk, remap=remap)

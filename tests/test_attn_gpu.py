@@ -20,12 +20,17 @@ def _rel_err(got, ref):
 
 def assert_close(got, ref, dtype):
     """Stated tolerance (SURVEY §8c-iv, FA2-vs-fp32 class error), per element:
-         bf16: |got-ref| <= 2e-2*RMS(ref) + 2^-7*|ref|   and mean|got-ref| <= 2e-3*RMS(ref)
+         bf16: |got-ref| <= 2e-2*RMS(ref) + 2^-7*|ref|   and mean|got-ref| <= 3e-3*RMS(ref)
          fp16: |got-ref| <= 5e-3*RMS(ref) + 2^-10*|ref|  and mean|got-ref| <= 5e-4*RMS(ref)
-    The |ref| term admits a 1-2 ulp flip of the 16-bit output rounding on large elements."""
+    The |ref| term admits a 1-2 ulp flip of the 16-bit output rounding on large elements.
+    The mean bound sits ~1.5x above the noise floor two CORRECT implementations have against
+    each other: P is rounded to bf16 (relative error 2^-9/sqrt(3) rms per term) relative to a
+    different running max in each (the reference rescales per tile, the oracle per tile, the
+    kernel lazily), which for uncorrelated V gives sqrt(2)*1.1e-3*RMS rms ~ 1.3e-3*RMS
+    mean-abs, plus the 16-bit output rounding."""
     got, ref = got.float().cpu(), ref.float().cpu()
     rms = ref.pow(2).mean().sqrt().item() + 1e-12
-    a, r, m = (2e-2, 2.0 ** -7, 2e-3) if dtype == torch.bfloat16 else (5e-3, 2.0 ** -10, 5e-4)
+    a, r, m = (2e-2, 2.0 ** -7, 3e-3) if dtype == torch.bfloat16 else (5e-3, 2.0 ** -10, 5e-4)
     d = (got - ref).abs()
     bad = d > (a * rms + r * ref.abs())
     assert not bad.any(), (int(bad.sum()), (d / rms).max().item())

@@ -73,7 +73,7 @@ def test_sampled_rows_against_fp32_torch(hy720p):
             rms = ref.pow(2).mean().sqrt()
             d = (got - ref).abs()
             assert (d <= 2e-2 * rms + 2.0 ** -7 * ref.abs()).all(), (h, m, (d / rms).max().item())
-            assert d.mean() <= 2e-3 * rms
+            assert d.mean() <= 3e-3 * rms  # see test_attn_gpu.assert_close for the noise floor
             worst = max(worst, (d / rms).max().item())
     print("worst max|err|/rms over sampled rows:", worst)
 

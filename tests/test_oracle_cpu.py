@@ -222,3 +222,14 @@ def test_install_hook_preseeds_reference_module_names():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_step_skip_schedule_matches_reference_lists():
+    """jenga_hyvideo.py:28 + stage switch: 23 computed steps of 50, drop rate switches after
+    step 25, 60 blocks per computed step -> 1380 hot-path calls per video."""
+    from jenga_b200 import dit_loop
+    s = dit_loop.schedule()
+    computed = [i for i, c, _ in s if c]
+    assert computed == list(dit_loop.NON_SKIP_STEPS) and len(computed) == 23
+    assert {d for i, c, d in s if i <= 25} == {0.7} and {d for i, c, d in s if i > 25} == {0.8}
+    assert len(computed) * (dit_loop.DOUBLE_BLOCKS + dit_loop.SINGLE_BLOCKS) == 1380

@@ -67,3 +67,23 @@ def test_gather_scatter_bit_exact():
     tab = synth.normal((t * h * w, 128), 78)
     gt = gather_tokens(tab.to(dev), h2l.to(dev))
     assert (gt.cpu() == tab[h2l]).all()
+
+
+def test_wan_prologue_matches_reference_golden():
+    """Fixture = WanRMSNorm + rope_apply from wan/modules/model_mul.py (make_golden.py), rounded
+    to bf16 like the operator does.  <= 1 bf16 ulp, >= 99.5 % bit-identical."""
+    import hashlib
+    from jenga_b200 import wan
+    gold = np.load(HERE / "golden" / "wan_prologue.npz")
+    c = synth.wan_prologue_case()
+    freqs = wan.rope_freqs(128)
+    sha = hashlib.sha256(np.ascontiguousarray(torch.view_as_real(freqs).numpy()).tobytes()).hexdigest()[:16]
+    assert sha == bytes(gold["freqs_sha"]).decode()  # same table as the reference builds
+    dev = "cuda"
+    for tag, x, w in (("q", c["xq"], c["wq"]), ("k", c["xk"], c["wk"])):
+        got = wan.norm_rope(x.to(dev), w.to(dev), c["H"], c["grid"], freqs, c["remap"], eps=1e-6).cpu()
+        ref = torch.from_numpy(gold[tag]).view(torch.bfloat16)
+        d = _ulp_diff_bf16(got, ref)
+        assert d.max() <= 1.0, (tag, d.max().item())
+        assert (got.view(torch.int16) == ref.view(torch.int16)).float().mean() >= 0.995
+    assert wan.block_counts(32760, 0.5) == (128, 12) and wan.block_counts(75600, 0.7) == (177, 28)
