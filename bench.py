@@ -222,7 +222,7 @@ def cpu_sample(wl, kind: str, budget_s: float = 12.0):
         mask[0, 0, i, nb_img:] = True
     flops = 4 * BLOCK * BLOCK * 128 * int(mask.sum())
     reps, t_total = 0, 0.0
-    while t_total < budget_s and reps < 50:
+    while reps == 0 or (t_total < budget_s and reps < 50):
         t0 = time.perf_counter()
         if kind == "port":
             orc.carved_attention_rows(q, k, v, mask, S, 128 ** -0.5, 0.0, nb_img)
@@ -275,7 +275,9 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": wl["name"], "sa_drop": wl["drop"], "p_remain": wl["p_remain"]},
+                "config": {"workload": wl["name"], "sa_drop": wl["drop"], "p_remain": wl["p_remain"],
+                           "text_blocks": wl["text_blocks"], "parallelism": "host cpu",
+                           "sample": "bounded: 1 head x 4 query blocks at the workload's key length and density"},
                 "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
                                  "sample": "torch SDPA + expanded block mask (reference CPU path, "
                                            "hyvideo/modules/attenion.py:102-107): " + sample},
