@@ -19,8 +19,10 @@
 // operands, V boxes are MN-major UMMA operands (no transpose anywhere).
 // CTAs are numbered head-major so that all CTAs in flight read the same head's K/V (59 MB at
 // 115K tokens) out of L2.
-#include "sm100_ptx.cuh"
-#include "jenga_internal.h"
+#include <cstdlib>
+#include <cstring>
+
+#include "carved_attn_common.cuh"
 
 #ifndef JENGA_POLY_EVERY
 #define JENGA_POLY_EVERY 3
@@ -32,6 +34,9 @@
 namespace jenga {
 
 namespace {
+
+using attn::BlockWalker;
+using attn::KernelParams;
 
 constexpr int kBlock = 128;           // rows per q block == keys per kv block
 constexpr int kHalf = 64;             // keys per half tile (the softmax / MMA pipelining unit)
@@ -63,44 +68,6 @@ enum BarId {
   NUM_BARS
 };
 static_assert(NUM_BARS * 8 + 4 <= 128, "barrier block overflow");
-
-struct KernelParams {
-  int heads;
-  int nq_sparse, nq_dense;
-  int nb_kv;
-  int mask_words;
-  int text_block_start;
-  long long q_rows;           // rows present in q / out
-  long long q_limit_sparse;   // sparse rows >= this produce zeros
-  long long kv_limit_sparse;  // key columns >= this are masked for sparse q blocks
-  long long kv_limit_dense;   // ... for dense q blocks
-  float qk_scale;             // sm_scale * log2(e)
-  float text_amp;
-  const uint32_t* mask_bits;
-  const int* seqlen_dev;      // optional: overrides q_limit_sparse / kv_limit_sparse
-  void* out;
-  long long o_stride_b, o_stride_s, o_stride_h;  // elements
-  int out_f32;                // 1: write fp32 (values still rounded through the MMA dtype)
-  int* err_flag;
-};
-
-// Walks the set bits of the row mask in ascending key-block order.
-struct BlockWalker {
-  const uint32_t* words;
-  int nwords;
-  int w;
-  uint32_t bits;
-  __device__ BlockWalker(const uint32_t* m, int n) : words(m), nwords(n), w(0), bits(n ? m[0] : 0) {}
-  __device__ int next() {  // -1 when exhausted
-    while (bits == 0) {
-      if (++w >= nwords) return -1;
-      bits = words[w];
-    }
-    const int j = __ffs(bits) - 1;
-    bits &= bits - 1;
-    return w * 32 + j;
-  }
-};
 
 // Pipeline of one CTA (one 128-row q block), per live key block j and key half h:
 //
@@ -547,16 +514,24 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
     if (q % 16) return set_error(JENGA_E_INVALID, "pointers must be 16-byte aligned");
   if (!(a->sm_scale > 0.f)) return set_error(JENGA_E_INVALID, "sm_scale must be positive");
 
+  // Kernel generation: v2 (default) or v3 via JENGA_ATTN_KERNEL (tuning switch, same results).
+  static const int gen = [] {
+    const char* e = std::getenv("JENGA_ATTN_KERNEL");
+    if (e && std::strcmp(e, "v3") == 0) return 3;      // 8 softmax warps
+    if (e && std::strcmp(e, "v3x4") == 0) return 34;   // 16 softmax warps
+    return 2;
+  }();
+  const int kv_box_rows = gen != 2 ? kBlock : kHalf;
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;
   if ((rc = make_tile_map(&tm_q, a->q, a->dtype, a->q_rows, a->heads, a->batch, a->q_stride_b,
                           a->q_stride_s, a->q_stride_h, kBlock)))
     return rc;
   if ((rc = make_tile_map(&tm_k, a->k, a->dtype, a->kv_rows, a->heads, a->batch, a->k_stride_b,
-                          a->k_stride_s, a->k_stride_h, kHalf)))
+                          a->k_stride_s, a->k_stride_h, kv_box_rows)))
     return rc;
   if ((rc = make_tile_map(&tm_v, a->v, a->dtype, a->kv_rows, a->heads, a->batch, a->v_stride_b,
-                          a->v_stride_s, a->v_stride_h, kHalf)))
+                          a->v_stride_s, a->v_stride_h, kv_box_rows)))
     return rc;
 
   KernelParams p{};
@@ -583,6 +558,9 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
   if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");
+  if (gen != 2)
+    return launch_carved_attn_v3(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16,
+                                 gen == 34 ? 4 : 2, stream);
   auto kern = a->dtype == JENGA_BF16 ? carved_attn_fwd_kernel<true> : carved_attn_fwd_kernel<false>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(carved_attn)");
