@@ -167,6 +167,15 @@ typedef struct JengaSelectArgs {
 int jenga_select_blocks(const JengaSelectArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Host <-> device staging for callers whose q/k/v live in (pinned) host memory: a strided 2-D
+ * copy on `stream` (cudaMemcpy2DAsync), used to move one head group of a [B,S,H,D] tensor
+ * (width = heads_in_group*D*elem bytes, height = B*S rows) so that transfers of group g+1
+ * overlap the attention of group g.  direction: 0 = host->device, 1 = device->host.
+ * ---------------------------------------------------------------------------------------- */
+int jenga_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                       int64_t width_bytes, int64_t rows, int32_t direction, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (a-5, a-6, part of a-8) HunyuanVideo attention prologue: per-head RMSNorm(q,k), RoPE(q,k)
  * on the image tokens, img||txt concatenation and block mean-pooling in one pass.
  * ref: hyvideo/modules/models_mul_block_gc_ha_multigpu.py:200-241 (double stream),

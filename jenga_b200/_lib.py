@@ -112,6 +112,9 @@ def _load() -> C.CDLL:
     lib.jenga_hy_prologue.restype = C.c_int
     lib.jenga_wan_prologue.argtypes = [C.POINTER(JengaWanPrologueArgs), C.c_void_p]
     lib.jenga_wan_prologue.restype = C.c_int
+    lib.jenga_copy2d_async.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_int32, C.c_void_p]
+    lib.jenga_copy2d_async.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 1:

@@ -209,7 +209,7 @@ def block_sparse_attention_variant(
     block_size_M: int = 128, block_size_N: int = 128, cu_seqlens_q=None, cu_seqlens_kv=None,
     max_seqlen_q=None, max_seqlen_kv=None, text_blocks=None, text_amp: float = 0.0,
     block_neighbor_list=None, shape_xfuse: bool = False, p_remain_rates=None,
-    first_frame_blocks: int = 0, return_mask_bits: bool = False,
+    first_frame_blocks: int = 0, return_mask_bits: bool = False, out: torch.Tensor | None = None,
 ):
     """AttenCarve operator, [B,S,H,D] in -> [B,S,H*D] (or [B,S,H,D] when shape_xfuse).
     Same arguments, defaults and quirks as the reference function of the same name; see the
@@ -265,7 +265,11 @@ def block_sparse_attention_variant(
                                   p_threshold=p_remain_rates, text_blocks=text_blocks,
                                   first_frame_blocks=first_frame_blocks if variant == "wan" else 0,
                                   nbr_bits=nbr)
-    out = torch.empty((B, S, H, D), dtype=out_dtype if variant == "wan" else q.dtype, device=q.device)
+    want_dtype = out_dtype if variant == "wan" else q.dtype
+    if out is None:
+        out = torch.empty((B, S, H, D), dtype=want_dtype, device=q.device)
+    elif out.shape != (B, S, H, D) or out.dtype != want_dtype or out.stride(3) != 1:
+        raise ValueError("out must be [B,S,H,D] in the result dtype with contiguous head_dim")
     a_out_dtype = out.dtype
     limit = S  # no cu_seqlens: seqlens = [context_size] (:336 / wan :452)
     o = _launch(q, k, v, mask_bits, normal_blocks, text_blocks, D ** -0.5, text_amp, normal_blocks,

@@ -160,3 +160,14 @@ extern "C" int jenga_hy_prologue(const JengaHyPrologueArgs* args, void* stream) 
 extern "C" int jenga_wan_prologue(const JengaWanPrologueArgs* args, void* stream) {
   return wan_prologue_impl(args, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int jenga_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                                  int64_t width_bytes, int64_t rows, int32_t direction, void* stream) {
+  if (!dst || !src || width_bytes <= 0 || rows <= 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+    return set_error(JENGA_E_INVALID, "copy2d: bad arguments");
+  const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  cudaError_t ce = cudaMemcpy2DAsync(dst, static_cast<size_t>(dst_pitch), src, static_cast<size_t>(src_pitch),
+                                     static_cast<size_t>(width_bytes), static_cast<size_t>(rows), kind,
+                                     static_cast<cudaStream_t>(stream));
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "cudaMemcpy2DAsync");
+}
