@@ -453,7 +453,7 @@ def main():
                        "p_remain": wl["p_remain"], "text_blocks": wl["text_blocks"],
                        "live_tiles": pop, "algorithmic_tflop_per_step": flops / 1e12,
                        "l2": "inputs (2.8 GB) larger than L2, no flush",
-                       "parallelism": "1 gpu" if world == 1 else f"ulysses{world}",
+                       "parallelism": "1 gpu" if world == 1 else f"ulysses{world} ({state['mode']})",
                        "hot_path_sec_per_video": ms * 1e-3 * wl["layers"] * wl["computed_steps"]},
             "clocks": clocks, "gpu_launches": launches * args.steps,
         }

@@ -110,6 +110,17 @@ typedef struct JengaAttnArgs {
   const int32_t* seqlen_dev;
   int32_t out_dtype; /* == dtype, or JENGA_F32 (wan variant returns the query dtype, :530-532) */
   int32_t* err_flag; /* device int, may be NULL: set non-zero by in-kernel watchdogs */
+  /* Fused Ulysses epilogue (sp_world > 0; ref hyvideo/modules/xdit_ring_atten.py:206-219 does
+   * the same data movement with two all-to-alls after the kernel).  q/k/v hold this rank's
+   * `heads` heads over the FULL sequence (image rows of all ranks in rank order, then the dense
+   * text rows).  out_peers_host[r] (HOST array of sp_world device pointers, peer-mapped) is the
+   * base of rank r's result buffer [sp_rows + dense rows, sp_heads_total, D]; each output row is
+   * stored directly into its owner's buffer (image row t -> rank t / sp_rows; dense rows ->
+   * every rank), at heads [sp_rank*heads, (sp_rank+1)*heads).  `out` is ignored.  The caller
+   * synchronises the ranks before reading (jenga_b200.ulysses.UlyssesFusedAttention). */
+  int32_t sp_world, sp_rank, sp_heads_total;
+  int64_t sp_rows;
+  const uint64_t* out_peers_host;
 } JengaAttnArgs;
 
 int jenga_carved_attn_fwd(const JengaAttnArgs* args, void* stream);
@@ -165,6 +176,26 @@ typedef struct JengaSelectArgs {
 } JengaSelectArgs;
 
 int jenga_select_blocks(const JengaSelectArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-12) Ulysses inbound exchange as ONE kernel of peer stores (ref xdit_ring_atten.py:120-131
+ * does it with four SeqAllToAll4D collectives + .contiguous() copies): this rank's image rows
+ * x[w][i, :, :] (w = q,k,v; i < n_loc; all `heads` heads) are written into every rank p's
+ * buffer at [w, rank*n_loc + i, 0:heads/world, :] <- heads [p*heads/world, (p+1)*heads/world),
+ * and the replicated text rows joint[w] into the LOCAL buffer at rows [world*n_loc, +n_text).
+ * peer_qkv_host[p] (HOST array) = peer-mapped base of rank p's [3, world*n_loc + n_text,
+ * heads/world, head_dim] buffer.  Element size 2 bytes.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct JengaUlyssesScatterArgs {
+  const void* x[3];
+  const void* joint[3]; /* may be NULL when n_text == 0 */
+  int64_t x_stride_s, joint_stride_s; /* element stride between tokens ([n, H, D] views) */
+  int32_t world, rank, heads, head_dim;
+  int64_t n_loc, n_text;
+  const uint64_t* peer_qkv_host;
+} JengaUlyssesScatterArgs;
+
+int jenga_ulysses_scatter(const JengaUlyssesScatterArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host <-> device staging for callers whose q/k/v live in (pinned) host memory: a strided 2-D

@@ -37,6 +37,17 @@ class JengaAttnArgs(C.Structure):
         ("kv_limit_dense", C.c_int64),
         ("seqlen_dev", C.c_void_p), ("out_dtype", C.c_int32),
         ("err_flag", C.c_void_p),
+        ("sp_world", C.c_int32), ("sp_rank", C.c_int32), ("sp_heads_total", C.c_int32),
+        ("sp_rows", C.c_int64), ("out_peers_host", C.c_void_p),
+    ]
+
+
+class JengaUlyssesScatterArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p * 3), ("joint", C.c_void_p * 3),
+        ("x_stride_s", C.c_int64), ("joint_stride_s", C.c_int64),
+        ("world", C.c_int32), ("rank", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("n_loc", C.c_int64), ("n_text", C.c_int64), ("peer_qkv_host", C.c_void_p),
     ]
 
 
@@ -115,6 +126,8 @@ def _load() -> C.CDLL:
     lib.jenga_copy2d_async.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                        C.c_int32, C.c_void_p]
     lib.jenga_copy2d_async.restype = C.c_int
+    lib.jenga_ulysses_scatter.argtypes = [C.POINTER(JengaUlyssesScatterArgs), C.c_void_p]
+    lib.jenga_ulysses_scatter.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 1:

@@ -210,6 +210,7 @@ def block_sparse_attention_variant(
     max_seqlen_q=None, max_seqlen_kv=None, text_blocks=None, text_amp: float = 0.0,
     block_neighbor_list=None, shape_xfuse: bool = False, p_remain_rates=None,
     first_frame_blocks: int = 0, return_mask_bits: bool = False, out: torch.Tensor | None = None,
+    sp_out: dict | None = None,
 ):
     """AttenCarve operator, [B,S,H,D] in -> [B,S,H*D] (or [B,S,H,D] when shape_xfuse).
     Same arguments, defaults and quirks as the reference function of the same name; see the
@@ -266,6 +267,11 @@ def block_sparse_attention_variant(
                                   first_frame_blocks=first_frame_blocks if variant == "wan" else 0,
                                   nbr_bits=nbr)
     want_dtype = out_dtype if variant == "wan" else q.dtype
+    if sp_out is not None:
+        # fused Ulysses epilogue: rows are stored into the owners' peer-mapped buffers
+        _launch(q, k, v, mask_bits, normal_blocks, text_blocks, D ** -0.5, text_amp, normal_blocks,
+                S, S, nb * BLOCK, None, seqlen_dev, q.dtype, sp_out=sp_out)
+        return mask_bits if return_mask_bits else None
     if out is None:
         out = torch.empty((B, S, H, D), dtype=want_dtype, device=q.device)
     elif out.shape != (B, S, H, D) or out.dtype != want_dtype or out.stride(3) != 1:
@@ -280,10 +286,11 @@ def block_sparse_attention_variant(
 
 
 def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_block_start,
-            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype):
+            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype, sp_out=None):
     B, Sq, H, D = q.shape
     a = JengaAttnArgs()
-    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.out = out.data_ptr() if out is not None else None
     a.dtype = _dtype_code(q)
     a.out_dtype = _lib.JENGA_F32 if out_dtype == torch.float32 else a.dtype
     a.batch, a.heads, a.head_dim = B, H, D
@@ -291,7 +298,12 @@ def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_bl
     a.q_stride_b, a.q_stride_s, a.q_stride_h = q.stride(0), q.stride(1), q.stride(2)
     a.k_stride_b, a.k_stride_s, a.k_stride_h = k.stride(0), k.stride(1), k.stride(2)
     a.v_stride_b, a.v_stride_s, a.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
-    a.o_stride_b, a.o_stride_s, a.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
+    if out is not None:
+        a.o_stride_b, a.o_stride_s, a.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
+    if sp_out is not None:
+        a.sp_world, a.sp_rank = sp_out["world"], sp_out["rank"]
+        a.sp_heads_total, a.sp_rows = sp_out["heads_total"], sp_out["rows"]
+        a.out_peers_host = C.addressof(sp_out["peers"])
     a.nq_sparse, a.nq_dense = nq_sparse, nq_dense
     a.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
     a.mask_words = mask_bits.shape[-1] if mask_bits is not None else 0

@@ -93,6 +93,49 @@ onehot_to_bits_kernel(const uint8_t* __restrict__ onehot, uint32_t* __restrict__
   if (lane == 0) bits[gw] = word;
 }
 
+// Ulysses inbound exchange: one pass over the local q,k,v, 16-byte stores into peer memory.
+struct ScatterParams {
+  const uint4* x[3];
+  const uint4* joint[3];
+  long long x_stride_v, joint_stride_v;  // uint4 units between tokens
+  int world, rank, heads, vec_per_head;  // vec_per_head = head_dim*2/16
+  long long n_loc, n_text;
+  unsigned long long peer[8];
+};
+__global__ void __launch_bounds__(256)
+ulysses_scatter_kernel(const ScatterParams p) {
+  const int w = blockIdx.y;  // 0:q 1:k 2:v
+  const int vec_per_row = p.heads * p.vec_per_head;
+  const int h_loc = p.heads / p.world;
+  const long long n_total = static_cast<long long>(p.world) * p.n_loc + p.n_text;
+  const long long img_vecs = p.n_loc * vec_per_row;
+  const long long txt_vecs = p.n_text * (static_cast<long long>(h_loc) * p.vec_per_head);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < img_vecs + txt_vecs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < img_vecs) {
+      const long long tok = i / vec_per_row;
+      const int c = static_cast<int>(i - tok * vec_per_row);
+      const int head = c / p.vec_per_head;
+      const int dst_rank = head / h_loc;
+      const int hl = head - dst_rank * h_loc;
+      const uint4 v = __ldg(p.x[w] + tok * p.x_stride_v + c);
+      uint4* dst = reinterpret_cast<uint4*>(p.peer[dst_rank]) +
+                   ((static_cast<long long>(w) * n_total + p.rank * p.n_loc + tok) * h_loc + hl) * p.vec_per_head +
+                   (c - head * p.vec_per_head);
+      *dst = v;
+    } else {
+      const long long k = i - img_vecs;
+      const int per_tok = h_loc * p.vec_per_head;
+      const long long tok = k / per_tok;
+      const int c = static_cast<int>(k - tok * per_tok);
+      const uint4 v = __ldg(p.joint[w] + tok * p.joint_stride_v + p.rank * per_tok + c);
+      uint4* dst = reinterpret_cast<uint4*>(p.peer[p.rank]) +
+                   (static_cast<long long>(w) * n_total + p.world * p.n_loc + tok) * per_tok + c;
+      *dst = v;
+    }
+  }
+}
+
 }  // namespace jenga
 
 using namespace jenga;
@@ -170,4 +213,31 @@ extern "C" int jenga_copy2d_async(void* dst, int64_t dst_pitch, const void* src,
                                      static_cast<size_t>(width_bytes), static_cast<size_t>(rows), kind,
                                      static_cast<cudaStream_t>(stream));
   return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "cudaMemcpy2DAsync");
+}
+
+extern "C" int jenga_ulysses_scatter(const JengaUlyssesScatterArgs* a, void* stream) {
+  if (!a || !a->x[0] || !a->x[1] || !a->x[2] || !a->peer_qkv_host)
+    return set_error(JENGA_E_INVALID, "ulysses_scatter: null pointer");
+  if (a->world <= 0 || a->world > 8 || a->rank < 0 || a->rank >= a->world || a->heads % a->world ||
+      a->head_dim % 8 || a->n_loc <= 0 || a->n_text < 0 || a->x_stride_s % 8 || a->joint_stride_s % 8)
+    return set_error(JENGA_E_INVALID, "ulysses_scatter: bad shape");
+  if (a->n_text > 0 && (!a->joint[0] || !a->joint[1] || !a->joint[2]))
+    return set_error(JENGA_E_INVALID, "ulysses_scatter: joint tensors missing");
+  ScatterParams p{};
+  for (int w = 0; w < 3; ++w) {
+    p.x[w] = static_cast<const uint4*>(a->x[w]);
+    p.joint[w] = static_cast<const uint4*>(a->joint[w]);
+  }
+  p.x_stride_v = a->x_stride_s / 8;
+  p.joint_stride_v = a->joint_stride_s / 8;
+  p.world = a->world; p.rank = a->rank; p.heads = a->heads; p.vec_per_head = a->head_dim / 8;
+  p.n_loc = a->n_loc; p.n_text = a->n_text;
+  for (int r = 0; r < a->world; ++r) p.peer[r] = a->peer_qkv_host[r];
+  const long long total = a->n_loc * a->heads * p.vec_per_head + a->n_text * (a->heads / a->world) * p.vec_per_head;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  dim3 grid(static_cast<unsigned>(blocks), 3);
+  ulysses_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "ulysses_scatter launch");
 }

@@ -410,10 +410,24 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     const bool in_tensor = q_row < p.q_rows;
     const bool zero_row = (n_tiles == 0) || (!dense && q_row >= q_limit_sparse);
     const float inv_l = zero_row ? 0.f : 1.0f / l_sum;
-    const long long o_off =
-        b * p.o_stride_b + q_row * p.o_stride_s + static_cast<long long>(h) * p.o_stride_h;
-    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + o_off;
-    float* orow32 = reinterpret_cast<float*>(p.out) + o_off;
+    // destination(s) of this row
+    long long o_off = b * p.o_stride_b + q_row * p.o_stride_s + static_cast<long long>(h) * p.o_stride_h;
+    uint16_t* obase = reinterpret_cast<uint16_t*>(p.out);
+    int n_dst = 1;  // > 1 only for replicated (text) rows under Ulysses
+    if (p.sp_world > 0) {
+      // Fused Ulysses exchange (ref xdit_ring_atten.py:206-219 does this with two all-to-alls
+      // after the kernel): image row t belongs to rank t / sp_rows; text rows go to every rank.
+      const long long n_img = p.sp_rows * p.sp_world;
+      const int gh = p.sp_rank * p.heads + h;
+      if (q_row < n_img) {
+        const int owner = static_cast<int>(q_row / p.sp_rows);
+        obase = reinterpret_cast<uint16_t*>(p.peer_out[owner]);
+        o_off = ((q_row - owner * p.sp_rows) * p.sp_heads_total + gh) * kHeadDim;
+      } else {
+        n_dst = p.sp_world;
+        o_off = ((p.sp_rows + (q_row - n_img)) * p.sp_heads_total + gh) * kHeadDim;
+      }
+    }
 #pragma unroll 1
     for (int cc = 0; cc < 128; cc += 32) {
       uint32_t o[32];
@@ -435,9 +449,13 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
             const float bb = zero_row ? 0.f : __uint_as_float(o[i + 2 * t + 1]) * inv_l;
             e[t] = pack2<kBF16>(a, bb);
           }
-          if (!p.out_f32) {
-            *reinterpret_cast<uint4*>(orow + cc + i) = v;
+          if (n_dst > 1) {
+            for (int r = 0; r < n_dst; ++r)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.peer_out[r]) + o_off + cc + i) = v;
+          } else if (!p.out_f32) {
+            *reinterpret_cast<uint4*>(obase + o_off + cc + i) = v;
           } else {  // wan/…:530-532: the 16-bit result is widened back to the query dtype
+            float* orow32 = reinterpret_cast<float*>(p.out) + o_off;
             float2 t0 = unpack2<kBF16>(e[0]), t1 = unpack2<kBF16>(e[1]);
             const float4 f0 = make_float4(t0.x, t0.y, t1.x, t1.y);
             t0 = unpack2<kBF16>(e[2]);
@@ -483,7 +501,7 @@ static int make_tile_map(CUtensorMap* map, const void* base, int dtype, long lon
 static bool stride_ok(long long s) { return s > 0 && (s * 2) % 16 == 0; }
 
 int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
-  if (!a || !a->q || !a->k || !a->v || !a->out) return set_error(JENGA_E_INVALID, "null pointer");
+  if (!a || !a->q || !a->k || !a->v || (!a->out && a->sp_world <= 0)) return set_error(JENGA_E_INVALID, "null pointer");
   if (a->dtype != JENGA_BF16 && a->dtype != JENGA_F16)
     return set_error(JENGA_E_INVALID, "dtype must be bf16 or f16");
   if (a->head_dim != kHeadDim)
@@ -505,8 +523,9 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   const long long strides[] = {a->q_stride_b, a->q_stride_s, a->q_stride_h, a->k_stride_b,
                                a->k_stride_s, a->k_stride_h, a->v_stride_b, a->v_stride_s,
                                a->v_stride_h, a->o_stride_b, a->o_stride_s, a->o_stride_h};
-  for (long long s : strides)
-    if (!stride_ok(s)) return set_error(JENGA_E_INVALID, "strides must be positive multiples of 8");
+  for (int i = 0; i < 12; ++i)
+    if (!stride_ok(strides[i]) && !(i >= 9 && a->sp_world > 0))
+      return set_error(JENGA_E_INVALID, "strides must be positive multiples of 8");
   if (a->out_dtype != a->dtype && a->out_dtype != JENGA_F32)
     return set_error(JENGA_E_INVALID, "out_dtype must equal dtype or be f32");
   const uintptr_t ptrs[] = {(uintptr_t)a->q, (uintptr_t)a->k, (uintptr_t)a->v, (uintptr_t)a->out};
@@ -548,6 +567,16 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   p.qk_scale = static_cast<float>(static_cast<double>(a->sm_scale) * 1.44269504);  // ref :172
   p.text_amp = a->text_amp;
   p.mask_bits = a->mask_bits;
+  if (a->sp_world > 0) {
+    if (a->sp_world > 8 || a->sp_rank < 0 || a->sp_rank >= a->sp_world || !a->out_peers_host || a->sp_rows <= 0 ||
+        a->sp_heads_total != a->heads * a->sp_world || a->batch != 1 || a->out_dtype != a->dtype)
+      return set_error(JENGA_E_INVALID, "bad Ulysses epilogue arguments");
+    p.sp_world = a->sp_world;
+    p.sp_rank = a->sp_rank;
+    p.sp_heads_total = a->sp_heads_total;
+    p.sp_rows = a->sp_rows;
+    for (int r = 0; r < a->sp_world; ++r) p.peer_out[r] = a->out_peers_host[r];
+  }
   p.seqlen_dev = a->seqlen_dev;
   p.out_f32 = a->out_dtype == JENGA_F32 ? 1 : 0;
   p.out = a->out;
@@ -558,6 +587,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
   if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");
+  if (gen != 2 && a->sp_world > 0)
+    return set_error(JENGA_E_UNSUPPORTED, "the Ulysses fused epilogue is built for kernel generation 2");
   if (gen != 2)
     return launch_carved_attn_v3(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16,
                                  gen == 34 ? 4 : 2, stream);

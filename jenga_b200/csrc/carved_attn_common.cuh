@@ -23,6 +23,12 @@ struct KernelParams {
   void* out;
   long long o_stride_b, o_stride_s, o_stride_h;  // elements
   int out_f32;                // 1: write fp32 (values still rounded through the MMA dtype)
+  // Ulysses fused epilogue (sp_world > 0): O rows are stored straight into the token owner's
+  // buffer over NVLink instead of `out`.  peer_out[r] = base of rank r's [sp_rows + dense rows,
+  // sp_heads_total, D] buffer; this rank's heads are [sp_rank*heads, (sp_rank+1)*heads).
+  int sp_world, sp_rank, sp_heads_total;
+  long long sp_rows;          // image rows owned per rank
+  unsigned long long peer_out[8];
   int* err_flag;
 };
 

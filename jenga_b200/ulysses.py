@@ -128,6 +128,95 @@ class UlyssesCarvedAttention:
         return torch.cat([img, txt], dim=1)
 
 
+class UlyssesFusedAttention:
+    """Same contract as UlyssesCarvedAttention, with the exchange fused into the kernels over
+    NVLink peer memory (torch symmetric memory provides the mapped pointers):
+
+      in : ONE kernel (jenga_ulysses_scatter) stores this rank's Q/K/V image rows into every
+           rank's [3, N+T, H/P, D] buffer with 16-byte peer stores — replaces three all-to-alls
+           and their .contiguous() staging copies; text rows are a local head-slice copy.
+      out: the attention kernel's epilogue stores each finished O row straight into the token
+           owner's [n_loc+T, H, D] buffer (text rows into every rank's) — replaces the
+           all-to-all, the all-gather and the permute copies.
+    Two device-side barriers per call (after the scatter, after the attention) order the peer
+    traffic; they also make buffer reuse across layers safe on a single stream."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self._bufs = {}
+
+    def _buffers(self, N, T, h, D, n_loc, H, dtype, dev):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        key = (N, T, h, D, n_loc, H, dtype, str(dev))
+        hit = self._bufs.get(key)
+        if hit is not None:
+            return hit
+        P = dist.get_world_size(self.group)
+        try:
+            symm.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        qkv = symm.empty((3, N + T, h, D), dtype=dtype, device=dev)
+        out = symm.empty((n_loc + T, H, D), dtype=dtype, device=dev)
+        h_qkv = symm.rendezvous(qkv, self.group.group_name)
+        h_out = symm.rendezvous(out, self.group.group_name)
+        p_qkv = (C.c_uint64 * P)(*[int(x) for x in h_qkv.buffer_ptrs])
+        p_out = (C.c_uint64 * P)(*[int(x) for x in h_out.buffer_ptrs])
+        self._bufs[key] = (qkv, out, h_qkv, h_out, p_qkv, p_out)
+        return self._bufs[key]
+
+    def __call__(self, attn, query, key, value, *, joint_tensor_query=None, joint_tensor_key=None,
+                 joint_tensor_value=None, joint_strategy="none", top_k=0, text_amp=0.0,
+                 block_neighbor_list=None, p_remain_rates=0.0, cu_seqlens_q=None, cu_seqlens_kv=None,
+                 **_unused):
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, lib
+        from .attention import _stream_ptr, block_sparse_attention_variant
+        P, r = _group_size_rank(self.group)
+        B, n, H, D = query.shape
+        if B != 1:
+            raise ValueError("the fused Ulysses path is built for batch 1 (what the pipelines run)")
+        h = H // P
+        joint = joint_tensor_query is not None
+        if joint and joint_strategy != "rear":
+            raise ValueError("only joint_strategy='rear' is built (attenion.py:181)")
+        T = joint_tensor_query.shape[1] if joint else 0
+        N = P * n
+        dev, dt = query.device, query.dtype
+        qkv, out, h_qkv, h_out, p_qkv, p_out = self._buffers(N, T, h, D, n, H, dt, dev)
+        a = _lib.JengaUlyssesScatterArgs()
+        xs = [t[0] for t in (query, key, value)]
+        for t in xs:
+            if t.stride(2) != 1 or t.stride(1) != D:
+                raise ValueError("q/k/v must be [1, n, H, D] views with contiguous heads")
+        a.x = (C.c_void_p * 3)(*[t.data_ptr() for t in xs])
+        a.x_stride_s = xs[0].stride(0)
+        if joint:
+            js = [t[0] for t in (joint_tensor_query, joint_tensor_key, joint_tensor_value)]
+            a.joint = (C.c_void_p * 3)(*[t.data_ptr() for t in js])
+            a.joint_stride_s = js[0].stride(0)
+        a.world, a.rank, a.heads, a.head_dim, a.n_loc, a.n_text = P, r, H, D, n, T
+        a.peer_qkv_host = C.addressof(p_qkv)
+        with torch.cuda.device(dev):
+            check(lib.jenga_ulysses_scatter(C.byref(a), _stream_ptr(dev)), "ulysses_scatter")
+        h_qkv.barrier(channel=0)
+        if cu_seqlens_q is not None:
+            valid = (cu_seqlens_q[1:2].to(device=dev, dtype=torch.int32) - n) + N
+            cu = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), valid,
+                            torch.full((1,), N + T, dtype=torch.int32, device=dev)])
+        else:
+            cu = None
+        sp = dict(world=P, rank=r, heads_total=H, rows=n, peers=p_out)
+        block_sparse_attention_variant("hyvideo", qkv[0][None], qkv[1][None], qkv[2][None], top_k,
+                                       cu_seqlens_q=cu, cu_seqlens_kv=cu, text_blocks=T // BLOCK,
+                                       text_amp=text_amp, block_neighbor_list=block_neighbor_list,
+                                       p_remain_rates=p_remain_rates, sp_out=sp)
+        h_out.barrier(channel=0)
+        return out[None].clone()  # the symmetric buffer is overwritten by the next call
+
+
 def my_parallel_attention(hybrid_seq_parallel_attn, q, k, v, img_q_len, img_kv_len, cu_seqlens_q,
                           cu_seqlens_kv, top_k=int(10e7), text_amp=0.0, block_neighbor_list=None,
                           p_remain_rates=0.0):
@@ -161,8 +250,11 @@ def bench_setup(wl, build_inputs, dev, rank, world):
     del full
     inp.update(q=None, k=None, v=None, top_k=top_k)
     torch.cuda.empty_cache()
-    return dict(q=q, k=k, v=v, cu=cu, n_loc=n_loc, top_k=top_k, inp=inp, sp=UlyssesCarvedAttention(),
-                world=world, rank=rank)
+    import os
+    fused = os.environ.get("JENGA_ULYSSES", "fused") != "nccl"
+    return dict(q=q, k=k, v=v, cu=cu, n_loc=n_loc, top_k=top_k, inp=inp,
+                sp=UlyssesFusedAttention() if fused else UlyssesCarvedAttention(),
+                world=world, rank=rank, mode="fused peer stores" if fused else "nccl all-to-all")
 
 
 def bench_step(wl, st):

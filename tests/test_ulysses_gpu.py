@@ -15,7 +15,7 @@ WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["JENGA_ROOT"]); sys.path.insert(0, os.path.join(os.environ["JENGA_ROOT"], "tests", "golden"))
 import synth
-from jenga_b200.ulysses import UlyssesCarvedAttention, my_parallel_attention
+from jenga_b200.ulysses import UlyssesCarvedAttention, UlyssesFusedAttention, my_parallel_attention
 from jenga_b200.attention import block_sparse_attention
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
@@ -36,6 +36,12 @@ full = block_sparse_attention(q, k, v, 2, cu_seqlens_q=cuf, cu_seqlens_kv=cuf, t
                               block_neighbor_list=nbr, p_remain_rates=0.3, text_blocks=2)
 torch.cuda.synchronize()
 ok = torch.equal(out[:, :n_loc], full[:, sl]) and torch.equal(out[:, n_loc:], full[:, n_img:])
+fz = UlyssesFusedAttention()
+for _ in range(2):  # twice: buffer reuse across calls
+    out2 = my_parallel_attention(fz, ql, kl, vl, n_loc, n_loc, cu, cu, top_k=2, text_amp=0.3,
+                                 block_neighbor_list=nbr, p_remain_rates=0.3)
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(out2, out)
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0: print("ULYSSES_OK" if t.item() == 1 else "ULYSSES_MISMATCH")
 dist.destroy_process_group()
