@@ -359,7 +359,7 @@ def main():
         ach = flops / (ams * 1e-3) / 1e12
         traffic = None
         tp = ROOT / "profiles" / "attn_traffic.json"
-        if tp.exists():
+        if tp.exists() and args.workload == "hy720p":
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
             except Exception:
@@ -452,7 +452,7 @@ def main():
             "config": {"workload": wl["name"], "sa_drop": wl["drop"], "top_k": inp["top_k"],
                        "p_remain": wl["p_remain"], "text_blocks": wl["text_blocks"],
                        "live_tiles": pop, "algorithmic_tflop_per_step": flops / 1e12,
-                       "l2": "inputs (2.8 GB) larger than L2, no flush",
+                       "l2": f"inputs ({3 * inp['S'] * inp['heads'] * 256 / 1e9:.1f} GB) larger than L2, no flush",
                        "parallelism": "1 gpu" if world == 1 else f"ulysses{world} ({state['mode']})",
                        "hot_path_sec_per_video": ms * 1e-3 * wl["layers"] * wl["computed_steps"]},
             "clocks": clocks, "gpu_launches": launches * args.steps,

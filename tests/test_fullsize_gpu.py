@@ -101,3 +101,91 @@ def test_gather_scatter_round_trip_full_size():
     assert torch.equal(g[0, idx], x[0, h2l.to(dev)[idx]])
     back = gather_tokens(g, l2h.to(dev))
     assert torch.equal(back, x)
+
+
+def _check_rows(q, k, v, out4, oh, n_img_blocks, seqlen, S_pad, rows_to_check, heads, text_blocks):
+    """fp32 torch evaluation of selected q blocks (sparse: reference Triton semantics; dense:
+    FlashAttention semantics over the zero-padded keys)."""
+    dev = q.device
+    qk_scale = torch.tensor((128 ** -0.5) * 1.44269504, dtype=torch.float32, device=dev)
+    S = q.shape[1]
+    for h in heads:
+        kh = torch.zeros(S_pad, 128, device=dev)
+        vh = torch.zeros(S_pad, 128, device=dev)
+        kh[:S], vh[:S] = k[0, :, h].float(), v[0, :, h].float()
+        for m in rows_to_check:
+            r0, r1 = m * 128, min((m + 1) * 128, S)
+            qm = q[0, r0:r1, h].float()
+            if m < n_img_blocks:
+                live = oh[0, h, m].nonzero().flatten()
+                cols = (live[:, None] * 128 + torch.arange(128, device=dev)[None]).flatten()
+                qt = (qm * qk_scale).to(torch.bfloat16).float()
+                s = (qt @ kh[cols].T).masked_fill(cols[None, :] >= seqlen, float("-inf"))
+                pr = torch.exp2(s - s.max(-1, keepdim=True).values)
+            else:
+                cols = torch.arange(S_pad, device=dev)
+                s = (qm @ kh.T) * (128 ** -0.5)
+                pr = torch.exp(s - s.max(-1, keepdim=True).values)
+            ref = (pr.to(torch.bfloat16).float() @ vh[cols]) / pr.sum(-1, keepdim=True)
+            valid = (torch.arange(r0, r1, device=dev) < seqlen) if m < n_img_blocks else torch.ones(r1 - r0, dtype=torch.bool, device=dev)
+            ref = torch.where(valid[:, None], ref, torch.zeros_like(ref))
+            got = out4[0, r0:r1, h].float()
+            rms = ref.pow(2).mean().sqrt()
+            d = (got - ref).abs()
+            assert (d <= 2e-2 * rms + 2.0 ** -7 * ref.abs()).all(), (h, m, (d / rms).max().item())
+            assert d.mean() <= 3e-3 * rms
+
+
+def test_wan_1_3b_full_size_fp32_inputs():
+    """BASELINE configs[0]: Wan2.1-1.3B 832x480x81f — q,k fp32 [1,32760,12,128] (rope_apply returns
+    .float()), v bf16, 8 zero-padded rows, sliced-gilbert adjacency, first-frame rule, fp32 output."""
+    import bench
+    from jenga_b200 import gilbert, wan
+    from jenga_b200.attention import bits_to_onehot, block_sparse_attention_variant
+    dev = torch.device("cuda", 0)
+    t, h, w = 21, 30, 52
+    S, H = t * h * w, 12
+    q = bench.synth_tokens(S, H, dev, 4321).float()
+    k = bench.synth_tokens(S, H, dev, 4322).float()
+    v = torch.randn(1, S, H, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(4323)).bfloat16()
+    nbr = gilbert.sliced_gilbert_block_neighbor_mapping(t, h, w)
+    top_k, ff = wan.block_counts(S, 0.5)
+    assert (top_k, ff) == (128, 12)
+    out, bits = block_sparse_attention_variant("wan", q, k, v, top_k, text_blocks=0, block_neighbor_list=nbr,
+                                               p_remain_rates=0.9, first_frame_blocks=ff, shape_xfuse=True,
+                                               return_mask_bits=True)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float32 and out.shape == (1, S, H, 128)
+    nb = 256
+    oh = bits_to_onehot(bits, nb)
+    assert oh[0, :, :ff, :ff].all()                                   # first-frame square (wan/…:400-406)
+    assert (oh[0] | ~nbr.to(dev)[None]).all()
+    assert int(oh.sum(-1).min()) >= top_k
+    # values are bf16-rounded before widening (wan/…:530-532)
+    assert torch.equal(out, out.bfloat16().float())
+    _check_rows(q.bfloat16(), k.bfloat16(), v, out, oh, nb, S, nb * 128, (0, 5, 128, 255), (0, 11), 0)
+
+
+def test_hyvideo_i2v_full_size_ragged():
+    """BASELINE configs[4] shape: 115200 image + 400 text tokens -> 904 blocks, text_blocks=4, the
+    last block has 112 zero-padded rows that text queries DO attend (SURVEY A-3)."""
+    import bench
+    from jenga_b200 import gilbert
+    from jenga_b200.attention import bits_to_onehot, block_sparse_attention_variant
+    dev = torch.device("cuda", 0)
+    n_img, T, H = 115200, 400, 4  # 4 of the 24 heads keep the test short; the shape per head is full size
+    S = n_img + T
+    q = bench.synth_tokens(S, H, dev, 5321)
+    k = bench.synth_tokens(S, H, dev, 5322)
+    v = torch.randn(1, S, H, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(5323)).bfloat16()
+    nbr = gilbert.gilbert_block_neighbor_mapping(32, 45, 80)
+    cu = torch.tensor([0, n_img + 300, S], dtype=torch.int32, device=dev)
+    top_k = int((1 - 0.75) * (n_img // 128))
+    out, bits = block_sparse_attention_variant("hyvideo_i2v", q, k, v, top_k, cu_seqlens_q=cu, cu_seqlens_kv=cu,
+                                               text_blocks=4, block_neighbor_list=nbr, p_remain_rates=0.3,
+                                               shape_xfuse=True, return_mask_bits=True)
+    torch.cuda.synchronize()
+    assert out.shape == (1, S, H, 128)
+    oh = bits_to_onehot(bits, 904)
+    assert oh[..., 900:904].all() and bits.shape[2] == 900
+    _check_rows(q, k, v, out, oh, 900, n_img + 300, 904 * 128, (0, 899, 900, 903), (0, 3), 4)
