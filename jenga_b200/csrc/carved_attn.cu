@@ -532,6 +532,10 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   for (uintptr_t q : ptrs)
     if (q % 16) return set_error(JENGA_E_INVALID, "pointers must be 16-byte aligned");
   if (!(a->sm_scale > 0.f)) return set_error(JENGA_E_INVALID, "sm_scale must be positive");
+  if (a->sp_world != 0 &&
+      (a->sp_world < 0 || a->sp_world > 8 || a->sp_rank < 0 || a->sp_rank >= a->sp_world || !a->out_peers_host ||
+       a->sp_rows <= 0 || a->sp_heads_total != a->heads * a->sp_world || a->batch != 1 || a->out_dtype != a->dtype))
+    return set_error(JENGA_E_INVALID, "bad Ulysses epilogue arguments");
 
   // Kernel generation: v2 (default) or v3 via JENGA_ATTN_KERNEL (tuning switch, same results).
   static const int gen = [] {
@@ -568,9 +572,6 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   p.text_amp = a->text_amp;
   p.mask_bits = a->mask_bits;
   if (a->sp_world > 0) {
-    if (a->sp_world > 8 || a->sp_rank < 0 || a->sp_rank >= a->sp_world || !a->out_peers_host || a->sp_rows <= 0 ||
-        a->sp_heads_total != a->heads * a->sp_world || a->batch != 1 || a->out_dtype != a->dtype)
-      return set_error(JENGA_E_INVALID, "bad Ulysses epilogue arguments");
     p.sp_world = a->sp_world;
     p.sp_rank = a->sp_rank;
     p.sp_heads_total = a->sp_heads_total;

@@ -120,8 +120,31 @@ __device__ __forceinline__ void norm_rope8(float (&x)[8], const float (&w)[8], b
 }
 
 template <bool kBF16>
-__global__ void __launch_bounds__(384)
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack2<kBF16>(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// Tokens are processed in groups of kGroup with all of a group's q/k/v loads issued before any
+// arithmetic: the kernel is a pure stream (37 KB in + out per token per CTA), so what matters is
+// bytes in flight per SM — ~1.7 us of HBM latency x 44 GB/s per SM ~ 75 KB.
+#ifndef JENGA_PRO_GROUP
+#define JENGA_PRO_GROUP 2
+#endif
+#ifndef JENGA_PRO_MINB
+#define JENGA_PRO_MINB 2
+#endif
+constexpr int kGroup = JENGA_PRO_GROUP;
+
+template <bool kBF16>
+__global__ void __launch_bounds__(384, JENGA_PRO_MINB)
 hy_prologue_kernel(const PrologueParams p) {
+  __shared__ float s_w[4][128];  // img_q, img_k, txt_q, txt_k norm weights
   const int blk = blockIdx.x;
   const int b = blockIdx.y;
   const int S = p.L + p.T;
@@ -130,6 +153,16 @@ hy_prologue_kernel(const PrologueParams p) {
   const int rows_per_iter = blockDim.x >> 4;  // (token, head) rows handled per pass
   const long long tok0 = static_cast<long long>(blk) * kBlock;
   const int n_tok = static_cast<int>(min(static_cast<long long>(kBlock), S - tok0));
+  const bool has_w = p.w_img_q != nullptr;
+  if (has_w) {
+    for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) {
+      const uint16_t* src = (i < 128) ? p.w_img_q : (i < 256) ? p.w_img_k : (i < 384) ? p.w_txt_q : p.w_txt_k;
+      const uint16_t raw = src[i & 127];
+      s_w[i >> 7][i & 127] = kBF16 ? __uint_as_float(static_cast<uint32_t>(raw) << 16)
+                                   : __half2float(__ushort_as_half(raw));
+    }
+  }
+  __syncthreads();
 
   // A thread always serves the same head set {h : (h - hslot) % rows_per_iter == 0} so its
   // pooling accumulators are per (head, chunk).  With H <= rows_per_iter (24 <= 24) that is
@@ -138,45 +171,60 @@ hy_prologue_kernel(const PrologueParams p) {
   // the two half-warps of a warp may serve different head counts: shuffle inside the half only
   const unsigned half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
   for (int h = hslot; h < p.H; h += rows_per_iter) {
-    float wq_i[8], wk_i[8], wq_t[8], wk_t[8];
-    const bool has_w = p.w_img_q != nullptr;
-    if (has_w) {
-      load8<kBF16>(p.w_img_q + d0, wq_i);
-      load8<kBF16>(p.w_img_k + d0, wk_i);
-      load8<kBF16>(p.w_txt_q + d0, wq_t);
-      load8<kBF16>(p.w_txt_k + d0, wk_t);
-    }
     float qsum[8], ksum[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) qsum[i] = ksum[i] = 0.f;
-#pragma unroll 2
-    for (int t = 0; t < n_tok; ++t) {
-      const long long tok = tok0 + t;
-      const bool is_img = tok < p.L;
-      const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
-                                   : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
-      const long long sw = is_img ? p.img_sw : p.txt_sw;
-      float q[8], k[8];
-      load8<kBF16>(src, q);
-      load8<kBF16>(src + sw, k);
-      const uint4 vraw = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
-      const float* cs = nullptr;
-      const float* sn = nullptr;
-      if (is_img && p.cos_t) {
-        const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
-        cs = p.cos_t + row * 128 + d0;
-        sn = p.sin_t + row * 128 + d0;
-      }
-      norm_rope8<kBF16>(q, is_img ? wq_i : wq_t, has_w, p.eps, cs, sn, half_mask);
-      norm_rope8<kBF16>(k, is_img ? wk_i : wk_t, has_w, p.eps, cs, sn, half_mask);
-      const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
-      *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
-      *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
-      *reinterpret_cast<uint4*>(p.v + o) = vraw;
+    for (int t0 = 0; t0 < n_tok; t0 += kGroup) {
+      uint4 rq[kGroup], rk[kGroup], rv[kGroup];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        qsum[i] += q[i];
-        ksum[i] += k[i];
+      for (int g = 0; g < kGroup; ++g) {
+        const long long tok = tok0 + t0 + g;
+        if (t0 + g < n_tok) {
+          const bool is_img = tok < p.L;
+          const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
+                                       : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
+          const long long sw = is_img ? p.img_sw : p.txt_sw;
+          rq[g] = __ldg(reinterpret_cast<const uint4*>(src));
+          rk[g] = __ldg(reinterpret_cast<const uint4*>(src + sw));
+          rv[g] = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kGroup; ++g) {
+        const long long tok = tok0 + t0 + g;
+        if (t0 + g < n_tok) {  // uniform across the CTA
+          const bool is_img = tok < p.L;
+          float q[8], k[8], wq[8], wk[8];
+          unpack8<kBF16>(rq[g], q);
+          unpack8<kBF16>(rk[g], k);
+          if (has_w) {
+            const float* wqs = s_w[is_img ? 0 : 2] + d0;
+            const float* wks = s_w[is_img ? 1 : 3] + d0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              wq[i] = wqs[i];
+              wk[i] = wks[i];
+            }
+          }
+          const float* cs = nullptr;
+          const float* sn = nullptr;
+          if (is_img && p.cos_t) {
+            const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
+            cs = p.cos_t + row * 128 + d0;
+            sn = p.sin_t + row * 128 + d0;
+          }
+          norm_rope8<kBF16>(q, wq, has_w, p.eps, cs, sn, half_mask);
+          norm_rope8<kBF16>(k, wk, has_w, p.eps, cs, sn, half_mask);
+          const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
+          *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
+          *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
+          *reinterpret_cast<uint4*>(p.v + o) = rv[g];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            qsum[i] += q[i];
+            ksum[i] += k[i];
+          }
+        }
       }
     }
     if (p.q_pool) {

@@ -74,14 +74,16 @@ class UlyssesCarvedAttention:
     (xdit_ring_atten.py:61-85).  `attn_fn` is injectable so the CPU tests can exercise the
     layout logic with the oracle; by default it is the sm_100a operator."""
 
-    def __init__(self, group=None, attn_fn=None):
+    def __init__(self, group=None, attn_fn=None, variant: str = "hyvideo"):
         self.group = group
         self._attn_fn = attn_fn
+        self.variant = variant  # "hyvideo" | "hyvideo_i2v" (ragged text: 400 tokens -> 4 blocks)
 
     def _attn(self, *a, **k):
         if self._attn_fn is None:
-            from .attention import block_sparse_attention
-            self._attn_fn = block_sparse_attention
+            from .attention import block_sparse_attention_variant
+            v = self.variant
+            self._attn_fn = lambda q, k_, v_, **kw: block_sparse_attention_variant(v, q, k_, v_, kw.pop("top_k"), **kw)
         return self._attn_fn(*a, **k)
 
     def __call__(self, attn, query, key, value, *, joint_tensor_query=None, joint_tensor_key=None,
@@ -120,7 +122,7 @@ class UlyssesCarvedAttention:
         out = self._attn(qkv[0], qkv[1], qkv[2], top_k=top_k, block_size_M=128, block_size_N=128,
                          cu_seqlens_q=cu, cu_seqlens_kv=cu, text_amp=text_amp,
                          block_neighbor_list=block_neighbor_list, p_remain_rates=p_remain_rates,
-                         shape_xfuse=True, **({"text_blocks": T // BLOCK} if joint else {"text_blocks": 0}))
+                         shape_xfuse=True, text_blocks=(T + BLOCK - 1) // BLOCK if joint else 0)
         img = heads_to_seq(out[:, :N], self.group)
         if not joint:
             return img
@@ -141,8 +143,9 @@ class UlyssesFusedAttention:
     Two device-side barriers per call (after the scatter, after the attention) order the peer
     traffic; they also make buffer reuse across layers safe on a single stream."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, variant: str = "hyvideo"):
         self.group = group if group is not None else dist.group.WORLD
+        self.variant = variant
         self._bufs = {}
 
     def _buffers(self, N, T, h, D, n_loc, H, dtype, dev):
@@ -209,8 +212,8 @@ class UlyssesFusedAttention:
         else:
             cu = None
         sp = dict(world=P, rank=r, heads_total=H, rows=n, peers=p_out)
-        block_sparse_attention_variant("hyvideo", qkv[0][None], qkv[1][None], qkv[2][None], top_k,
-                                       cu_seqlens_q=cu, cu_seqlens_kv=cu, text_blocks=T // BLOCK,
+        block_sparse_attention_variant(self.variant, qkv[0][None], qkv[1][None], qkv[2][None], top_k,
+                                       cu_seqlens_q=cu, cu_seqlens_kv=cu, text_blocks=(T + BLOCK - 1) // BLOCK,
                                        text_amp=text_amp, block_neighbor_list=block_neighbor_list,
                                        p_remain_rates=p_remain_rates, sp_out=sp)
         h_out.barrier(channel=0)

@@ -1,0 +1,40 @@
+"""Times the HBM-bound kernels of the path at HY-720p size and prints achieved GB/s vs the
+measured HBM peak (MEASURED_PEAKS.json hbm_gbs)."""
+import json, sys, torch
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from jenga_b200 import gilbert
+from jenga_b200.attention import block_pool, select_blocks, neighbour_bits
+from jenga_b200.hyvideo import attention_prologue, gather_tokens
+dev = torch.device("cuda", 0)
+peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+L, T, H = 115200, 256, 24
+S = L + T
+def timeit(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+res = {}
+img = torch.randn(1, L, 3 * H * 128, device=dev).bfloat16()
+txt = torch.randn(1, T, 3 * H * 128, device=dev).bfloat16()
+ws = [torch.ones(128, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+cos = torch.rand(L, 128, device=dev); sin = torch.rand(L, 128, device=dev)
+ms = timeit(lambda: attention_prologue(img, txt, H, *ws, eps=1e-6, freqs_cis=(cos, sin)))
+byt = 2 * (3 * S * H * 128 * 2) + 2 * L * 128 * 4
+res["hy_prologue"] = (ms, byt)
+q, k, v, pools = attention_prologue(img, txt, H, *ws, eps=1e-6, freqs_cis=(cos, sin))
+ms = timeit(lambda: block_pool(k, 902)); res["block_pool(k)"] = (ms, S * H * 128 * 2)
+x = torch.randn(1, L, 3072, device=dev).bfloat16()
+l2h, h2l = gilbert.mapping_tensors(32, 45, 80); h2l = h2l.to(dev)
+ms = timeit(lambda: gather_tokens(x, h2l)); res["gather_rows"] = (ms, 2 * L * 3072 * 2)
+nbr = neighbour_bits(gilbert.block_neighbor_mapping(32, 45, 80), dev)
+qp, kp = pools
+ms = timeit(lambda: select_blocks(qp[:, :, :900].contiguous(), kp, n_img=900, nb=902, top_k=270, p_threshold=0.3, text_blocks=2, nbr_bits=nbr))
+res["select_blocks"] = (ms, 0)
+for k_, (ms, b) in res.items():
+    print(f"{k_:16s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}" if b else f"{k_:16s} {ms:8.3f} ms")

@@ -1,0 +1,88 @@
+"""C-ABI argument validation and error reporting, exercised WITHOUT a GPU: every entry point
+must reject bad arguments with a negative code and a message before it touches CUDA, and the
+host-only entry points must work."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from jenga_b200 import _lib
+from jenga_b200._lib import JengaAttnArgs, JengaSelectArgs, lib
+
+E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
+
+
+def _err():
+    return lib.jenga_last_error().decode()
+
+
+def _attn_args(**over):
+    a = JengaAttnArgs()
+    a.q = a.k = a.v = a.out = 0x10000  # never dereferenced on the validation paths
+    a.dtype = _lib.JENGA_BF16
+    a.out_dtype = _lib.JENGA_BF16
+    a.batch, a.heads, a.head_dim = 1, 2, 128
+    a.q_rows = a.kv_rows = 256
+    for t in "qkvo":
+        setattr(a, f"{t}_stride_b", 256 * 256)
+        setattr(a, f"{t}_stride_s", 256)
+        setattr(a, f"{t}_stride_h", 128)
+    a.nq_sparse, a.nq_dense = 0, 2
+    a.sm_scale = 0.1
+    a.kv_limit_sparse = a.q_limit_sparse = a.kv_limit_dense = 256
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize("over,code,needle", [
+    (dict(head_dim=64), E_UNSUPPORTED, "head_dim"),
+    (dict(dtype=_lib.JENGA_F32), E_INVALID, "dtype"),
+    (dict(q=None), E_INVALID, "null"),
+    (dict(nq_sparse=0, nq_dense=0), E_INVALID, "query blocks"),
+    (dict(nq_dense=3), E_INVALID, "exceed"),
+    (dict(q_stride_s=250), E_INVALID, "strides"),
+    (dict(q=0x10008), E_INVALID, "aligned"),
+    (dict(sm_scale=0.0), E_INVALID, "sm_scale"),
+    (dict(nq_sparse=1, nq_dense=1, mask_bits=None), E_INVALID, "mask_bits"),
+    (dict(out_dtype=_lib.JENGA_F16), E_INVALID, "out_dtype"),
+    (dict(sp_world=9), E_INVALID, "Ulysses"),
+])
+def test_attention_argument_validation(over, code, needle):
+    a = _attn_args(**over)
+    rc = lib.jenga_carved_attn_fwd(C.byref(a), None)
+    assert rc == code, (rc, _err())
+    assert needle.lower() in _err().lower(), _err()
+
+
+def test_attention_without_a_device_reports_cuda_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc = lib.jenga_carved_attn_fwd(C.byref(_attn_args()), None)
+    assert rc == E_CUDA and _err()
+
+
+def test_select_and_pool_validation():
+    s = JengaSelectArgs()
+    assert lib.jenga_select_blocks(C.byref(s), None) == E_INVALID
+    s.q_pool = s.k_pool = s.out_bits = 0x1000
+    s.dtype, s.batch_heads, s.head_dim, s.nq, s.nk_pool, s.n_img, s.nb = 0, 1, 128, 4, 4, 4, 6
+    s.mask_words = 0
+    assert lib.jenga_select_blocks(C.byref(s), None) == E_INVALID and "mask_words" in _err()
+    assert lib.jenga_block_pool(None, None, None, 0, 0, 1, 1, 128, 128, 0, 0, 0, 1, None) == E_INVALID
+    # n_blocks beyond the rows
+    assert lib.jenga_block_pool(0x1000, 0x1000, None, 0, 0, 1, 1, 128, 128, 16384, 128, 128, 2, None) == E_INVALID
+    assert lib.jenga_gather_rows(0x1000, 0x1000, 0x1000, 4, 4, 24, 1, 96, 96, None) == E_INVALID  # row not x16
+    assert lib.jenga_mask_onehot_to_bits(0x1000, 0x1000, 4, 40, 1, None) == E_INVALID            # words too small
+    assert lib.jenga_copy2d_async(0x1000, 8, 0x1000, 16, 16, 4, 0, None) == E_INVALID               # pitch < width
+
+
+def test_gilbert_host_entry_points_validate_and_run():
+    assert lib.jenga_gilbert_mapping_host(0, 4, 4, 0, None, None) == E_INVALID
+    a = np.zeros(8, dtype=np.int64)
+    assert lib.jenga_gilbert_mapping_host(0, 2, 4, 0, a.ctypes.data, None) == E_INVALID and "empty" in _err()
+    assert lib.jenga_gilbert_mapping_host(1, 2, 4, 0, a.ctypes.data, None) == 0
+    assert sorted(a.tolist()) == list(range(8))
+    assert lib.jenga_gilbert_xyz2d(5, 0, 0, 4, 4, 4) == -1  # out of bounds
+    assert lib.jenga_gilbert_block_neighbors_host(1, 2, 4, 0, 0, a.ctypes.data) == E_INVALID
