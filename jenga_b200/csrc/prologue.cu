@@ -85,10 +85,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // x (8 channels of one head row, spread over 16 lanes) -> normed, weighted, optionally rotated;
-// values are left rounded to the 16-bit dtype (as floats).
+// values are left rounded to the 16-bit dtype (as floats).  c/s: this thread's 8 cos/sin values.
 template <bool kBF16>
 __device__ __forceinline__ void norm_rope8(float (&x)[8], const float (&w)[8], bool has_w, float eps,
-                                           const float* cs, const float* sn, unsigned half_mask) {
+                                           bool rotate, const float4 (&cs)[2], const float4 (&sn)[2],
+                                           unsigned half_mask) {
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
@@ -101,13 +102,9 @@ __device__ __forceinline__ void norm_rope8(float (&x)[8], const float (&w)[8], b
     if (has_w) n = rnd<kBF16>(__fmul_rn(n, w[i]));
     x[i] = n;
   }
-  if (cs) {
-    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs));
-    const float4 c1 = __ldg(reinterpret_cast<const float4*>(cs) + 1);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn));
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sn) + 1);
-    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  if (rotate) {
+    const float c[8] = {cs[0].x, cs[0].y, cs[0].z, cs[0].w, cs[1].x, cs[1].y, cs[1].z, cs[1].w};
+    const float s[8] = {sn[0].x, sn[0].y, sn[0].z, sn[0].w, sn[1].x, sn[1].y, sn[1].z, sn[1].w};
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
@@ -134,7 +131,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 // arithmetic: the kernel is a pure stream (37 KB in + out per token per CTA), so what matters is
 // bytes in flight per SM — ~1.7 us of HBM latency x 44 GB/s per SM ~ 75 KB.
 #ifndef JENGA_PRO_GROUP
-#define JENGA_PRO_GROUP 2
+#define JENGA_PRO_GROUP 1
 #endif
 #ifndef JENGA_PRO_MINB
 #define JENGA_PRO_MINB 2
@@ -176,6 +173,7 @@ hy_prologue_kernel(const PrologueParams p) {
     for (int i = 0; i < 8; ++i) qsum[i] = ksum[i] = 0.f;
     for (int t0 = 0; t0 < n_tok; t0 += kGroup) {
       uint4 rq[kGroup], rk[kGroup], rv[kGroup];
+      float4 rc[kGroup][2], rs[kGroup][2];  // the token's cos / sin for this thread's 8 channels
 #pragma unroll
       for (int g = 0; g < kGroup; ++g) {
         const long long tok = tok0 + t0 + g;
@@ -187,6 +185,15 @@ hy_prologue_kernel(const PrologueParams p) {
           rq[g] = __ldg(reinterpret_cast<const uint4*>(src));
           rk[g] = __ldg(reinterpret_cast<const uint4*>(src + sw));
           rv[g] = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
+          if (is_img && p.cos_t) {
+            const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
+            const float4* cp = reinterpret_cast<const float4*>(p.cos_t + row * 128 + d0);
+            const float4* sp = reinterpret_cast<const float4*>(p.sin_t + row * 128 + d0);
+            rc[g][0] = __ldg(cp);
+            rc[g][1] = __ldg(cp + 1);
+            rs[g][0] = __ldg(sp);
+            rs[g][1] = __ldg(sp + 1);
+          }
         }
       }
 #pragma unroll
@@ -206,15 +213,9 @@ hy_prologue_kernel(const PrologueParams p) {
               wk[i] = wks[i];
             }
           }
-          const float* cs = nullptr;
-          const float* sn = nullptr;
-          if (is_img && p.cos_t) {
-            const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
-            cs = p.cos_t + row * 128 + d0;
-            sn = p.sin_t + row * 128 + d0;
-          }
-          norm_rope8<kBF16>(q, wq, has_w, p.eps, cs, sn, half_mask);
-          norm_rope8<kBF16>(k, wk, has_w, p.eps, cs, sn, half_mask);
+          const bool rotate = is_img && p.cos_t != nullptr;
+          norm_rope8<kBF16>(q, wq, has_w, p.eps, rotate, rc[g], rs[g], half_mask);
+          norm_rope8<kBF16>(k, wk, has_w, p.eps, rotate, rc[g], rs[g], half_mask);
           const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
           *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
           *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);

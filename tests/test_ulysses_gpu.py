@@ -42,6 +42,22 @@ for _ in range(2):  # twice: buffer reuse across calls
                                  block_neighbor_list=nbr, p_remain_rates=0.3)
     torch.cuda.synchronize()
     ok = ok and torch.equal(out2, out)
+# I2V-shaped joint tensors: 400 text tokens (ragged: 4 text blocks with 112 zero-padded rows)
+from jenga_b200.attention import block_sparse_attention_variant
+T2 = 400
+tq = synth.normal((1, T2, H, 128), 811).bfloat16().to(dev); tk = synth.normal((1, T2, H, 128), 812).bfloat16().to(dev)
+tv = synth.normal((1, T2, H, 128), 813).bfloat16().to(dev)
+ql2 = torch.cat([q[:, sl], tq], 1); kl2 = torch.cat([k[:, sl], tk], 1); vl2 = torch.cat([v[:, sl], tv], 1)
+cu2 = torch.tensor([0, n_loc + 300, n_loc + T2], dtype=torch.int32, device=dev)
+cuf2 = torch.tensor([0, n_img + 300, n_img + T2], dtype=torch.int32, device=dev)
+qf = torch.cat([q[:, :n_img], tq], 1); kf = torch.cat([k[:, :n_img], tk], 1); vf = torch.cat([v[:, :n_img], tv], 1)
+full2 = block_sparse_attention_variant("hyvideo_i2v", qf, kf, vf, 2, cu_seqlens_q=cuf2, cu_seqlens_kv=cuf2, text_blocks=4,
+                                       text_amp=0.0, block_neighbor_list=nbr, p_remain_rates=0.3)
+for cls in (UlyssesCarvedAttention, UlyssesFusedAttention):
+    o2 = my_parallel_attention(cls(variant="hyvideo_i2v"), ql2, kl2, vl2, n_loc, n_loc, cu2, cu2, top_k=2, text_amp=0.0,
+                               block_neighbor_list=nbr, p_remain_rates=0.3)
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(o2[:, :n_loc], full2[:, sl]) and torch.equal(o2[:, n_loc:], full2[:, n_img:])
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0: print("ULYSSES_OK" if t.item() == 1 else "ULYSSES_MISMATCH")
 dist.destroy_process_group()
