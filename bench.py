@@ -408,6 +408,37 @@ def main():
                "matches_device_resident_result": e2e_ok}
         del hq, hk, hv, hout, pipe, ref_out
 
+    if not args.no_e2e and world > 1:
+        # every rank stages ITS token slice (all heads) + the replicated text rows from pinned host
+        # memory, runs the sequence-parallel operator and returns its slice of the result to the host
+        hq, hk, hv = (state[n].cpu().pin_memory() for n in ("q", "k", "v"))
+        dq, dk, dv = (torch.empty_like(state[n]) for n in ("q", "k", "v"))
+        hout = torch.empty((1, state["q"].shape[1], inp["heads"] * 128), dtype=torch.bfloat16).pin_memory()
+        def e2e_step():
+            dq.copy_(hq, non_blocking=True)
+            dk.copy_(hk, non_blocking=True)
+            dv.copy_(hv, non_blocking=True)
+            st2 = dict(state, q=dq, k=dk, v=dv)
+            hout.copy_(ulysses.bench_step(wl, st2), non_blocking=True)
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        n_it = max(3, min(args.steps, 5))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n_it):
+            e2e_step()
+        b1.record()
+        barrier()
+        ems = b0.elapsed_time(b1) / n_it
+        t = torch.tensor([ems], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = t.item()
+        e2e = {"value": flops / (ems * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ems,
+               "h2d_bytes_per_step": world * sum(x.numel() * x.element_size() for x in (hq, hk, hv)),
+               "d2h_bytes_per_step": world * hout.numel() * hout.element_size(),
+               "api": "ulysses.my_parallel_attention on per-rank pinned host slices (max over ranks)"}
+
     dit = None
     if args.dit_loop > 0 and world == 1 and wl["variant"] == "hyvideo":
         from jenga_b200 import dit_loop
