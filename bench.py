@@ -379,7 +379,8 @@ def main():
         from jenga_b200.host_pipeline import HostPipelinedAttention
         hq, hk, hv = (x.cpu().pin_memory() for x in (inp["q"], inp["k"], inp["v"]))
         hout = torch.empty_like(hq).pin_memory()
-        groups = 6 if inp["heads"] % 6 == 0 else (4 if inp["heads"] % 4 == 0 else 1)
+        groups = int(os.environ.get("JENGA_E2E_GROUPS", "0")) or (
+            12 if inp["heads"] % 12 == 0 else (4 if inp["heads"] % 4 == 0 else 1))  # measured: 12 groups best at H=24
         pipe = HostPipelinedAttention(1, inp["S"], inp["heads"], 128, torch.bfloat16, dev, groups=groups,
                                       variant=wl["variant"])
         kw = dict(cu_seqlens_q=inp["cu"], cu_seqlens_kv=inp["cu"], text_blocks=wl["text_blocks"],

@@ -27,6 +27,14 @@
 #ifndef JENGA_POLY_EVERY
 #define JENGA_POLY_EVERY 3
 #endif
+#ifndef JENGA_RELAXED_PRODUCER
+#define JENGA_RELAXED_PRODUCER 0
+#endif
+#if JENGA_RELAXED_PRODUCER
+#define JENGA_PRODUCER_WAIT mbar_wait_relaxed
+#else
+#define JENGA_PRODUCER_WAIT mbar_wait
+#endif
 #ifndef JENGA_QK_FULL
 #define JENGA_QK_FULL 0
 #endif
@@ -167,7 +175,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
           // half are contiguous: serves two N=64 operands or one N=128 operand.
           const int row0 = blk * kBlock + hh * kHalf;
           uint8_t* dst = sK + hh * kKVBoxBytes;
-          mbar_wait(&bars[K_EMPTY0 + hh], par, p.err_flag);
+          JENGA_PRODUCER_WAIT(&bars[K_EMPTY0 + hh], par, p.err_flag);
           mbar_arrive_expect_tx(&bars[K_FULL0 + hh], kKVSlotBytes);
           tma_load_4d(dst, &tm_k, &bars[K_FULL0 + hh], 0, row0, h, b);
           tma_load_4d(dst + 2 * kKVBoxBytes, &tm_k, &bars[K_FULL0 + hh], 64, row0, h, b);
@@ -176,7 +184,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
         for (int hh = 0; hh < 2; ++hh) {
           const int row0 = blk * kBlock + hh * kHalf;
           uint8_t* dst = sV + hh * kKVSlotBytes;
-          mbar_wait(&bars[V_EMPTY0 + hh], par, p.err_flag);
+          JENGA_PRODUCER_WAIT(&bars[V_EMPTY0 + hh], par, p.err_flag);
           mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVSlotBytes);
           tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
           tma_load_4d(dst + kKVBoxBytes, &tm_v, &bars[V_FULL0 + hh], 64, row0, h, b);

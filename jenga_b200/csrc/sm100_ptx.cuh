@@ -8,6 +8,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#ifndef JENGA_PRODUCER_SLEEP_NS
+#define JENGA_PRODUCER_SLEEP_NS 100
+#endif
+
 namespace jenga {
 
 // ---------------------------------------------------------------------------------------------
@@ -76,6 +80,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
 #pragma unroll 1
     for (int i = 0; i < 256; ++i)
       if (mbar_try_wait(bar, parity)) return;
+    if ((clock64() - t0) > (1ll << 31)) {
+      if (err_flag) atomicExch(err_flag, JENGA_DEV_WATCHDOG);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// Same contract, for waiters with slack (the TMA producer runs a ring ahead of its consumers):
+// sleeps between probes so the spinning warp does not compete for issue slots with the softmax
+// warp that shares its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int* err_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      __nanosleep(JENGA_PRODUCER_SLEEP_NS);
+      if (mbar_try_wait(bar, parity)) return;
+    }
     if ((clock64() - t0) > (1ll << 31)) {
       if (err_flag) atomicExch(err_flag, JENGA_DEV_WATCHDOG);
       __threadfence_system();
