@@ -57,6 +57,21 @@ def workload(name: str, drop: float):
                     grid=(21, 30, 52), sliced=1, heads=12, text_tokens=0, text_valid=0,
                     text_blocks=0, p_remain=0.9, drop=0.5, variant="wan", text_amp=0.0,
                     first_frame=(21 * 30 * 52 + 127) // 128 // 21, layers=30, computed_steps=60)
+    if name == "hy_turbo_s0":  # BASELINE configs[2], stage 0 of Jenga-Turbo: 0.75x latent grid, text_amp on
+        return dict(name="HunyuanVideo Jenga-Turbo stage 0 layer (grid 32x33x60, q,k,v [1,63616,24,128])",
+                    grid=(32, 33, 60), sliced=0, heads=24, text_tokens=256, text_valid=180,
+                    text_blocks=2, p_remain=0.3, drop=0.75, variant="hyvideo", text_amp=0.431,
+                    first_frame=0, layers=60, computed_steps=12)
+    if name == "hy_i2v":  # BASELINE configs[4] shape: 400 text tokens -> 4 text blocks, ragged S
+        return dict(name="HunyuanVideo-I2V 720x1280x125f layer (q,k,v [1,115600,24,128])",
+                    grid=(32, 45, 80), sliced=0, heads=24, text_tokens=400, text_valid=300,
+                    text_blocks=4, p_remain=0.3, drop=0.75, variant="hyvideo_i2v", text_amp=0.0,
+                    first_frame=0, layers=60, computed_steps=24)
+    if name == "wan14b":  # BASELINE configs[3]
+        return dict(name="Wan2.1-14B 1280x720x81f layer (q,k,v [1,75600,40,128])",
+                    grid=(21, 45, 80), sliced=1, heads=40, text_tokens=0, text_valid=0,
+                    text_blocks=0, p_remain=0.8, drop=0.7, variant="wan", text_amp=0.0,
+                    first_frame=(21 * 45 * 80 + 127) // 128 // 21, layers=40, computed_steps=100)
     if name == "tiny":  # CI / smoke
         return dict(name="tiny 8x16x16 grid, 4 heads", grid=(8, 16, 16), sliced=0, heads=4,
                     text_tokens=256, text_valid=180, text_blocks=2, p_remain=0.3, drop=drop,
@@ -101,6 +116,7 @@ def build_inputs(wl, dev, heads=None, seed=1234):
     if wl["variant"] == "wan":
         top_k = math.ceil(int(nb_img * (1 - wl["drop"])))       # wan/modules/model_mul.py:162-164
         cu = None
+        q, k = q.float(), k.float()  # rope_apply returns .float() (wan/modules/model_mul.py:71)
     else:
         top_k = int((1 - wl["drop"]) * (n_img // BLOCK))          # models_mul…:242
         cu = torch.tensor([0, n_img + wl["text_valid"], S], dtype=torch.int32, device=dev)
@@ -340,10 +356,11 @@ def main():
         from jenga_b200 import attention as A
         _, bits = run_operator(wl, inp, return_bits=True)
         S, nb_img = inp["S"], inp["nb_img"]
-        out = torch.empty_like(inp["q"])
+        aq, ak = (x if x.dtype == torch.bfloat16 else x.bfloat16() for x in (inp["q"], inp["k"]))
+        out = torch.empty_like(aq)
         seq = inp["cu"][1:2].contiguous() if inp["cu"] is not None else None
         def attn_only():
-            A._launch(inp["q"], inp["k"], inp["v"], bits, nb_img, wl["text_blocks"], 128 ** -0.5, wl["text_amp"],
+            A._launch(aq, ak, inp["v"], bits, nb_img, wl["text_blocks"], 128 ** -0.5, wl["text_amp"],
                       nb_img, S, S, ((S + 127) // 128) * 128, out, seq, torch.bfloat16)
         for _ in range(3):
             attn_only()
@@ -377,7 +394,8 @@ def main():
         # Public API: jenga_b200.host_pipeline.HostPipelinedAttention — the operator is per-head
         # independent, so head groups are staged H2D / computed / drained D2H on three streams.
         from jenga_b200.host_pipeline import HostPipelinedAttention
-        hq, hk, hv = (x.cpu().pin_memory() for x in (inp["q"], inp["k"], inp["v"]))
+        # (wan: q,k are staged as bf16 here; the device-resident `value` leg keeps the fp32 inputs)
+        hq, hk, hv = (x.to(torch.bfloat16).cpu().pin_memory() for x in (inp["q"], inp["k"], inp["v"]))
         hout = torch.empty_like(hq).pin_memory()
         groups = int(os.environ.get("JENGA_E2E_GROUPS", "0")) or (
             12 if inp["heads"] % 12 == 0 else (4 if inp["heads"] % 4 == 0 else 1))  # measured: 12 groups best at H=24
@@ -391,7 +409,8 @@ def main():
         for _ in range(2):
             e2e_step()
         torch.cuda.synchronize()
-        ref_out = run_operator(wl, inp).view(1, inp["S"], inp["heads"], 128)
+        ref_out = run_operator(wl, inp, q=inp["q"].to(torch.bfloat16), k=inp["k"].to(torch.bfloat16))
+        ref_out = ref_out.view(1, inp["S"], inp["heads"], 128)
         torch.cuda.synchronize()
         e2e_ok = bool(torch.equal(hout, ref_out.cpu()))
         n_it = max(3, min(args.steps, 5))
