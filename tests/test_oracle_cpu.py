@@ -233,3 +233,21 @@ def test_step_skip_schedule_matches_reference_lists():
     assert computed == list(dit_loop.NON_SKIP_STEPS) and len(computed) == 23
     assert {d for i, c, d in s if i <= 25} == {0.7} and {d for i, c, d in s if i > 25} == {0.8}
     assert len(computed) * (dit_loop.DOUBLE_BLOCKS + dit_loop.SINGLE_BLOCKS) == 1380
+
+
+def test_install_launcher_runs_a_script_with_the_hook(tmp_path):
+    """`python -m jenga_b200.install script.py args…` — the launcher form of the drop-in hook."""
+    import subprocess
+    script = tmp_path / "fake_jenga_script.py"
+    script.write_text(
+        "import sys\n"
+        "from gilbert import gilbert_mapping, gilbert_block_neighbor_mapping\n"
+        "import flash_attn\n"
+        "from hyvideo.modules.attention_block_triton_diffres import block_sparse_attention\n"
+        "l2h, h2l = gilbert_mapping(4, 6, 8)\n"
+        "print('HOOK', l2h[:4], flash_attn.__version__, block_sparse_attention.__doc__, sys.argv[1:])\n")
+    r = subprocess.run([sys.executable, "-m", "jenga_b200.install", str(script), "--video-size", "720"],
+                       capture_output=True, text=True, cwd=str(ROOT), timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "HOOK [0, 1, 26, 25]" in r.stdout and "jenga_b200 drop-in (hyvideo variant)" in r.stdout
+    assert "['--video-size', '720']" in r.stdout

@@ -107,3 +107,43 @@ def test_host_pipeline_equals_device_operator():
         pipe(hq, hk, hv, hout, 3, **kw)
         torch.cuda.synchronize()
         assert torch.equal(hout, ref.cpu())
+
+
+def test_wan_self_attention_composition():
+    """wan.self_attention == norm_rope(q), norm_rope(k) -> block_sparse_attention (wan variant)."""
+    from jenga_b200 import wan
+    from jenga_b200.attention import block_sparse_attention_variant
+    dev = "cuda"
+    f, h, w = 4, 8, 16   # 512 tokens = 4 blocks
+    L, H = f * h * w, 2
+    xq = synth.normal((1, L, H * 128), 71).bfloat16().to(dev)
+    xk = synth.normal((1, L, H * 128), 72).bfloat16().to(dev)
+    v = synth.normal((1, L, H, 128), 73).bfloat16().to(dev)
+    wq = (1 + 0.1 * synth.normal((H * 128,), 74)).to(dev)
+    wk = (1 + 0.1 * synth.normal((H * 128,), 75)).to(dev)
+    freqs = wan.rope_freqs(128)
+    nbr = synth.band_neighbours(4)
+    out = wan.self_attention(xq, xk, v, wq, wk, H, (f, h, w), freqs, 0.5, p_remain_rates=0.8, block_neighbor_list=nbr)
+    q = wan.norm_rope(xq, wq, H, (f, h, w), freqs)
+    k = wan.norm_rope(xk, wk, H, (f, h, w), freqs)
+    top_k, ff = wan.block_counts(L, 0.5)
+    ref = block_sparse_attention_variant("wan", q, k, v, top_k, text_blocks=0, block_neighbor_list=nbr,
+                                         p_remain_rates=0.8, first_frame_blocks=ff, shape_xfuse=True)
+    torch.cuda.synchronize()
+    assert out.shape == (1, L, H, 128) and torch.equal(out, ref)
+
+
+def test_dit_loop_harness_runs_the_schedule():
+    from jenga_b200 import dit_loop, gilbert
+    dev = "cuda"
+    t, h, w = 2, 8, 16  # 256 image tokens
+    L, T, H = t * h * w, 256, 2
+    img = synth.normal((1, L, 3 * H * 128), 81).bfloat16().to(dev)
+    txt = synth.normal((1, T, 3 * H * 128), 82).bfloat16().to(dev)
+    ws = [torch.ones(128, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+    cos = torch.cos(synth.normal((L, 128), 83)).to(dev)
+    sin = torch.sin(synth.normal((L, 128), 83)).to(dev)
+    nbr = gilbert.gilbert_block_neighbor_mapping(t, h, w)
+    cu = torch.tensor([0, L + 180, L + T], dtype=torch.int32, device=dev)
+    sec, calls = dit_loop.run_hot_path_loop(img, txt, H, ws, (cos, sin), nbr, cu, max_computed_steps=2)
+    assert calls == 2 * 60 and sec > 0
