@@ -254,10 +254,28 @@ def bench_setup(wl, build_inputs, dev, rank, world):
     inp.update(q=None, k=None, v=None, top_k=top_k)
     torch.cuda.empty_cache()
     import os
+    import sys
     fused = os.environ.get("JENGA_ULYSSES", "fused") != "nccl"
-    return dict(q=q, k=k, v=v, cu=cu, n_loc=n_loc, top_k=top_k, inp=inp,
-                sp=UlyssesFusedAttention() if fused else UlyssesCarvedAttention(),
-                world=world, rank=rank, mode="fused peer stores" if fused else "nccl all-to-all")
+    st = dict(q=q, k=k, v=v, cu=cu, n_loc=n_loc, top_k=top_k, inp=inp, world=world, rank=rank)
+    if fused:
+        # Both modes are GPU paths of this library.  The fused one needs peer-mapped symmetric
+        # memory; if the rendezvous is refused on this box (no P2P), every rank agrees to use NCCL.
+        ok = 1
+        try:
+            st["sp"] = UlyssesFusedAttention()
+            bench_step(wl, st)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            print(f"[bench] rank {rank}: fused Ulysses unavailable ({type(e).__name__}: {e}); using NCCL",
+                  file=sys.stderr)
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        fused = bool(t.item())
+    if not fused:
+        st["sp"] = UlyssesCarvedAttention()
+    st["mode"] = "fused peer stores" if fused else "nccl all-to-all"
+    return st
 
 
 def bench_step(wl, st):
