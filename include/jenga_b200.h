@@ -173,9 +173,16 @@ typedef struct JengaSelectArgs {
   int32_t nbr_rows, nbr_words;
   uint32_t* out_bits;
   int32_t* out_counts;
+  /* Optional score workspace (device): batch_heads*nq*n_img floats
+   * (jenga_select_blocks_workspace_bytes).  With it, and n_img <= 1024, the call runs as a tiled
+   * pooled-score GEMM + a one-warp-per-row selection kernel (same results, ~3x faster); without
+   * it a single fused kernel is used. */
+  void* workspace;
+  int64_t workspace_bytes;
 } JengaSelectArgs;
 
 int jenga_select_blocks(const JengaSelectArgs* args, void* stream);
+int64_t jenga_select_blocks_workspace_bytes(int32_t batch_heads, int32_t nq, int32_t n_img);
 
 /* ------------------------------------------------------------------------------------------
  * (a-12) Ulysses inbound exchange as ONE kernel of peer stores (ref xdit_ring_atten.py:120-131

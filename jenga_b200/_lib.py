@@ -60,6 +60,7 @@ class JengaSelectArgs(C.Structure):
         ("text_blocks", C.c_int32), ("first_frame_blocks", C.c_int32),
         ("nbr_bits", C.c_void_p), ("nbr_rows", C.c_int32), ("nbr_words", C.c_int32),
         ("out_bits", C.c_void_p), ("out_counts", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -119,6 +120,8 @@ def _load() -> C.CDLL:
     lib.jenga_block_pool.restype = C.c_int
     lib.jenga_select_blocks.argtypes = [C.POINTER(JengaSelectArgs), C.c_void_p]
     lib.jenga_select_blocks.restype = C.c_int
+    lib.jenga_select_blocks_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.jenga_select_blocks_workspace_bytes.restype = C.c_int64
     lib.jenga_hy_prologue.argtypes = [C.POINTER(JengaHyPrologueArgs), C.c_void_p]
     lib.jenga_hy_prologue.restype = C.c_int
     lib.jenga_wan_prologue.argtypes = [C.POINTER(JengaWanPrologueArgs), C.c_void_p]

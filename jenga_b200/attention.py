@@ -159,7 +159,8 @@ def neighbour_bits(block_neighbor_list: torch.Tensor, device) -> torch.Tensor:
 
 def select_blocks(q_pool: torch.Tensor, k_pool: torch.Tensor, *, n_img: int, nb: int, top_k: int,
                   p_threshold: float, text_blocks: int, first_frame_blocks: int = 0,
-                  nbr_bits: torch.Tensor | None = None, return_counts: bool = False):
+                  nbr_bits: torch.Tensor | None = None, return_counts: bool = False,
+                  use_workspace: bool = True):
     """Pooled scores -> per-(head, query block) bit rows of attended key blocks
     (ref …triton_diffres.py:227-293; wan first-frame rule :400-406)."""
     _require_cuda(q_pool, k_pool)
@@ -181,6 +182,13 @@ def select_blocks(q_pool: torch.Tensor, k_pool: torch.Tensor, *, n_img: int, nb:
         a.nbr_bits, a.nbr_rows, a.nbr_words = None, 0, 0
     a.out_bits = bits.data_ptr()
     a.out_counts = counts.data_ptr() if counts is not None else None
+    ws = None
+    if use_workspace and n_img <= 1024:
+        nbytes = lib.jenga_select_blocks_workspace_bytes(B * H, nq, n_img)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=q_pool.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    else:
+        a.workspace, a.workspace_bytes = None, 0
     with torch.cuda.device(q_pool.device):
         check(lib.jenga_select_blocks(C.byref(a), _stream_ptr(q_pool.device)), "select_blocks")
     return (bits, counts) if return_counts else bits

@@ -241,3 +241,8 @@ extern "C" int jenga_ulysses_scatter(const JengaUlyssesScatterArgs* a, void* str
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "ulysses_scatter launch");
 }
+
+extern "C" int64_t jenga_select_blocks_workspace_bytes(int32_t batch_heads, int32_t nq, int32_t n_img) {
+  if (batch_heads <= 0 || nq <= 0 || n_img <= 0) return 0;
+  return static_cast<int64_t>(batch_heads) * nq * n_img * static_cast<int64_t>(sizeof(float));
+}

@@ -402,6 +402,213 @@ select_blocks_kernel(const SelectParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-kernel fast path (n_img <= 1024, caller-provided score workspace):
+//   pooled_scores_kernel : smem-tiled fp32 GEMM  scores = round(round(qp kp^T) * D^-1/2)
+//   select_rows_kernel   : one warp per row — softmax, 32-bit register bitonic sort of the
+//                          probabilities, cut, then selection by threshold with ties taken in
+//                          index order (== a stable descending sort of (prob, index)).
+// Same arithmetic, in the same order, as select_blocks_kernel: the dot products accumulate
+// over d ascending with fmaf, so both paths produce identical bit rows.
+// ------------------------------------------------------------------------------------------
+template <int kDtype>
+__global__ void __launch_bounds__(256)
+pooled_scores_kernel(const uint16_t* __restrict__ q_pool, const uint16_t* __restrict__ k_pool,
+                     float* __restrict__ scores, int nq, int nk_pool, int n_img, int D) {
+  // 64 x 64 output tile per CTA, K = D = 128 resident in shared memory, 4 x 4 outputs per thread
+  extern __shared__ float sm_sc[];
+  float* As = sm_sc;                // [128][64 + 4]
+  float* Bs = sm_sc + 128 * 68;     // [128][64 + 4]
+  const int bh = blockIdx.z;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  for (int i = t; i < 64 * 16; i += 256) {
+    const int row = i >> 4, chunk = i & 15;
+    uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+    if (m0 + row < nq) va = __ldg(reinterpret_cast<const uint4*>(q_pool + (static_cast<size_t>(bh) * nq + m0 + row) * D) + chunk);
+    if (n0 + row < n_img) vb = __ldg(reinterpret_cast<const uint4*>(k_pool + (static_cast<size_t>(bh) * nk_pool + n0 + row) * D) + chunk);
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      As[(chunk * 8 + 2 * e) * 68 + row] = from_bits16<kDtype>(static_cast<uint16_t>(wa[e] & 0xffffu));
+      As[(chunk * 8 + 2 * e + 1) * 68 + row] = from_bits16<kDtype>(static_cast<uint16_t>(wa[e] >> 16));
+      Bs[(chunk * 8 + 2 * e) * 68 + row] = from_bits16<kDtype>(static_cast<uint16_t>(wb[e] & 0xffffu));
+      Bs[(chunk * 8 + 2 * e + 1) * 68 + row] = from_bits16<kDtype>(static_cast<uint16_t>(wb[e] >> 16));
+    }
+  }
+  __syncthreads();
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < 128; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(As + k * 68 + ty * 4);
+    const float4 b = *reinterpret_cast<const float4*>(Bs + k * 68 + tx * 4);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+  const float inv_sqrt_d = static_cast<float>(1.0 / sqrt(static_cast<double>(D)));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= nq) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < n_img)
+        scores[(static_cast<size_t>(bh) * nq + m) * n_img + n] =
+            round_to<kDtype>(round_to<kDtype>(acc[i][j]) * inv_sqrt_d);  // ref :227
+    }
+  }
+}
+
+// 32-bit descending bitonic sort, lane L owns sorted positions [32L, 32L+32)
+__device__ __forceinline__ void warp_bitonic_desc_u32(uint32_t (&key)[32], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 1024; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int lj = j >> 5;
+        const bool keep_max = ((lane & lj) == 0) == (((lane << 5) & k) == 0);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], lj);
+          key[r] = keep_max ? max(key[r], other) : min(key[r], other);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          if ((r & j) == 0) {
+            const int r2 = r | j;
+            const bool desc = (k < 32) ? ((r & k) == 0) : (((lane << 5) & k) == 0);
+            const uint32_t a = key[r], b = key[r2];
+            const uint32_t hi = max(a, b), lo = min(a, b);
+            key[r] = desc ? hi : lo;
+            key[r2] = desc ? lo : hi;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+select_rows_kernel(const float* __restrict__ scores, const SelectParams p) {
+  __shared__ uint32_t s_bits_all[4][64];  // up to 2048 key blocks per row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rowid = static_cast<long long>(blockIdx.x) * 4 + warp;  // (bh, m) flattened
+  const long long total_rows = p.rows_per_cta;  // (field reused: total number of rows)
+  if (rowid >= total_rows) return;
+  const int bh = static_cast<int>(rowid / p.nq);
+  const int m = static_cast<int>(rowid - static_cast<long long>(bh) * p.nq);
+  uint32_t* bits = s_bits_all[warp];
+  for (int w = lane; w < p.words; w += 32) bits[w] = 0;
+  __syncwarp();
+  const float* sc = scores + rowid * p.n_img;
+  // softmax in fp32 over the ranked blocks (ref :238), element j = q*32 + lane
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int j = q * 32 + lane;
+    v[q] = j < p.n_img ? __ldg(sc + j) : -INFINITY;
+    mx = fmaxf(mx, v[q]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int j = q * 32 + lane;
+    v[q] = j < p.n_img ? expf(v[q] - mx) : 0.f;
+    sum += v[q];
+  }
+  // same summation tree as select_blocks_kernel: per-lane strided partials, then butterfly
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  uint32_t key[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int j = q * 32 + lane;
+    v[q] = j < p.n_img ? v[q] / sum : 0.f;          // probabilities (>= 0: bit order == value order)
+    key[q] = j < p.n_img ? __float_as_uint(v[q]) : 0u;
+  }
+  warp_bitonic_desc_u32(key, lane);
+  // cumulative probability in sorted order (ref :242-246), lane chunks in rank order
+  float part = 0.f;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) part += __uint_as_float(key[q]);
+  float prefix = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, prefix, o);
+    if (lane >= o) prefix += t;
+  }
+  float run = prefix - part;
+  int local = 0;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    run += __uint_as_float(key[q]);
+    if (lane * 32 + q < p.n_img && run <= p.p_threshold) ++local;
+  }
+  int tot = local;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  const int n = min(max(tot + 1, p.top_k), p.n_img);  // ref :247-250
+  // threshold = n-th largest probability; how many strictly larger
+  uint32_t tau_local = 0;
+  int gt_local = 0;
+#pragma unroll
+  for (int q = 0; q < 32; ++q)
+    if (lane * 32 + q == n - 1) tau_local = key[q];
+  const uint32_t tau = __shfl_sync(0xffffffffu, tau_local, (n - 1) >> 5);
+#pragma unroll
+  for (int q = 0; q < 32; ++q)
+    if (lane * 32 + q < n && key[q] > tau) ++gt_local;
+  int gt = gt_local;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gt += __shfl_xor_sync(0xffffffffu, gt, o);
+  const int need_ties = n - gt;  // members of the tie group at the cut, taken in index order
+  int taken = 0;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int j = q * 32 + lane;
+    const uint32_t pb = __float_as_uint(v[q]);
+    const bool valid = j < p.n_img;
+    const bool is_tie = valid && pb == tau;
+    const uint32_t tm = __ballot_sync(0xffffffffu, is_tie);
+    const int rank = taken + __popc(tm & ((1u << lane) - 1u));
+    const bool sel = valid && (pb > tau || (is_tie && rank < need_ties));
+    const uint32_t sm = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0 && q < p.words) bits[q] = sm;  // word q covers blocks [32q, 32q+32)
+    taken += __popc(tm);
+  }
+  __syncwarp();
+  for (int w = lane; w < p.words; w += 32) {
+    uint32_t val = bits[w];
+    const int lo = w * 32;
+    auto range_bits = [&](int a, int b) -> uint32_t {
+      const int s0 = max(a, lo), e0 = min(b, lo + 32);
+      if (e0 <= s0) return 0u;
+      const uint32_t hi_mask = (e0 - lo) >= 32 ? 0xffffffffu : ((1u << (e0 - lo)) - 1u);
+      return hi_mask & ~((s0 - lo) > 0 ? ((1u << (s0 - lo)) - 1u) : 0u);
+    };
+    if (p.nbr_bits && m < p.nbr_rows && w < p.nbr_words)
+      val |= p.nbr_bits[static_cast<size_t>(m) * p.nbr_words + w] & range_bits(0, p.n_img);
+    if (m < p.first_frame_blocks) val |= range_bits(0, min(p.first_frame_blocks, p.nb));
+    if (p.text_blocks > 0) val |= range_bits(p.n_img, min(p.n_img + p.text_blocks, p.nb));
+    p.out_bits[rowid * p.words + w] = val;
+  }
+  if (p.out_counts && lane == 0) p.out_counts[rowid] = n;
+}
+
 }  // namespace
 
 int block_pool_impl(const void* x, void* pooled, void* cast_out, int in_dtype, int out_dtype,
@@ -448,6 +655,30 @@ int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream) {
   if (a->mask_words * 32 < a->nb) return set_error(JENGA_E_INVALID, "select_blocks: mask_words too small");
   if (a->top_k < 0 || a->text_blocks < 0 || a->first_frame_blocks < 0)
     return set_error(JENGA_E_INVALID, "select_blocks: negative count");
+  if (a->workspace && a->n_img <= 1024 && a->mask_words <= 64 && a->head_dim == 128) {
+    const size_t need = static_cast<size_t>(a->batch_heads) * a->nq * a->n_img * sizeof(float);
+    if (static_cast<size_t>(a->workspace_bytes) < need)
+      return set_error(JENGA_E_WORKSPACE, "select_blocks: workspace %lld < %zu bytes", (long long)a->workspace_bytes, need);
+    float* scores = static_cast<float*>(a->workspace);
+    dim3 g1((a->n_img + 63) / 64, (a->nq + 63) / 64, a->batch_heads);
+    const int smem1 = 2 * 128 * 68 * 4;
+    auto k1 = a->dtype == JENGA_BF16 ? pooled_scores_kernel<JENGA_BF16> : pooled_scores_kernel<JENGA_F16>;
+    cudaError_t ce = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(pooled_scores)");
+    k1<<<g1, 256, smem1, stream>>>(static_cast<const uint16_t*>(a->q_pool), static_cast<const uint16_t*>(a->k_pool),
+                                   scores, a->nq, a->nk_pool, a->n_img, a->head_dim);
+    SelectParams p{};
+    p.nq = a->nq; p.n_img = a->n_img; p.nb = a->nb; p.words = a->mask_words; p.top_k = a->top_k;
+    p.p_threshold = a->p_threshold; p.text_blocks = a->text_blocks; p.first_frame_blocks = a->first_frame_blocks;
+    p.nbr_bits = a->nbr_bits; p.nbr_rows = a->nbr_rows; p.nbr_words = a->nbr_words;
+    p.out_bits = a->out_bits; p.out_counts = a->out_counts;
+    const long long rows = static_cast<long long>(a->batch_heads) * a->nq;
+    if (rows > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "select_blocks: too many rows");
+    p.rows_per_cta = static_cast<int>(rows);  // (reused field: total rows for select_rows_kernel)
+    select_rows_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, stream>>>(scores, p);
+    ce = cudaGetLastError();
+    return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "select_blocks (2-kernel) launch");
+  }
   int npow2 = 32;
   while (npow2 < a->n_img) npow2 <<= 1;
   const bool reg_sort = a->n_img <= 1024;  // register-resident 1024-wide sort

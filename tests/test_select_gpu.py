@@ -72,3 +72,25 @@ def test_selection_large_random_vs_oracle():
     assert (inter / union).mean() >= 0.99
     assert (got.sum(-1) == ref.sum(-1)).float().mean() >= 0.98
     assert (got[..., n_img:] == ref[..., n_img:]).all()
+
+
+@pytest.mark.parametrize("n_img,n_txt,top_k,p,first", [(900, 2, 270, 0.3, 0), (256, 0, 128, 0.9, 12),
+                                                     (37, 4, 5, 0.5, 0), (1024, 2, 1, 0.05, 0)])
+def test_two_kernel_path_is_bit_identical_to_fused_kernel(n_img, n_txt, top_k, p, first):
+    """With a score workspace the selection runs as GEMM + one-warp-per-row kernel; without it as
+    one fused kernel.  Same arithmetic in the same order: bit rows and counts must be identical,
+    including rows with exact probability ties at the cut (duplicated key blocks)."""
+    from jenga_b200.attention import select_blocks
+    H, nb = 3, n_img + n_txt
+    g = torch.Generator().manual_seed(n_img)
+    qp = (torch.randn(1, H, n_img, 128, generator=g) * 1.5).bfloat16().cuda()
+    kp = (torch.randn(1, H, nb, 128, generator=g) * 1.5).bfloat16().cuda()
+    kp[:, :, 1:n_img:3] = kp[:, :, 0:n_img - 1:3][:, :, :kp[:, :, 1:n_img:3].shape[2]]  # duplicated blocks -> ties
+    nbr = (torch.randint(0, 2**31 - 1, (n_img, (nb + 31) // 32), generator=g, dtype=torch.int64) &
+           torch.randint(0, 2**31 - 1, (n_img, (nb + 31) // 32), generator=g, dtype=torch.int64)).int().cuda()
+    kw = dict(n_img=n_img, nb=nb, top_k=top_k, p_threshold=p, text_blocks=n_txt, first_frame_blocks=first,
+              nbr_bits=nbr, return_counts=True)
+    b1, c1 = select_blocks(qp, kp, use_workspace=True, **kw)
+    b0, c0 = select_blocks(qp, kp, use_workspace=False, **kw)
+    assert torch.equal(c0, c1)
+    assert torch.equal(b0, b1), int((b0 != b1).sum())
