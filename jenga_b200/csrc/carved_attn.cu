@@ -161,7 +161,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0 && elect_one()) {
       mbar_arrive_expect_tx(&bars[Q_FULL], kQTileBytes);
       tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, static_cast<int>(q_row0), h, b);
       tma_load_4d(sQ + kQHalfBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b);
@@ -193,7 +193,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
   } else if (warp == 1) {
     // =============================== tcgen05 issuer ===============================
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, /*b_mn_major=*/false, 128, kHalf);
       constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, /*b_mn_major=*/true, 128, kHeadDim);
       // K-major SW128 operands: 8-row groups are 1024 B apart (SBO); LBO unused (=16 B).
@@ -550,6 +550,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
     const char* e = std::getenv("JENGA_ATTN_KERNEL");
     if (e && std::strcmp(e, "v3") == 0) return 3;      // 8 softmax warps
     if (e && std::strcmp(e, "v3x4") == 0) return 34;   // 16 softmax warps
+    if (e && std::strcmp(e, "v4") == 0) return 4;      // two softmax streams, N=128 MMAs
+    if (e && std::strcmp(e, "v5") == 0) return 5;      // ... and two threads per row
     return 2;
   }();
   const int kv_box_rows = gen != 2 ? kBlock : kHalf;
@@ -596,8 +598,12 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
   if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");
+  if (gen == 5)
+    return launch_carved_attn_v5(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
+  if (gen == 4)
+    return launch_carved_attn_v4(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
   if (gen != 2 && a->sp_world > 0)
-    return set_error(JENGA_E_UNSUPPORTED, "the Ulysses fused epilogue is built for kernel generation 2");
+    return set_error(JENGA_E_UNSUPPORTED, "the Ulysses fused epilogue is not built for kernel generation 3");
   if (gen != 2)
     return launch_carved_attn_v3(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16,
                                  gen == 34 ? 4 : 2, stream);

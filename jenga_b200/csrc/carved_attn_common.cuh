@@ -56,4 +56,10 @@ struct BlockWalker {
 // kernel generation 3 (carved_attn_v3.cu): 1 CTA/SM, Q in TMEM, N=128 MMAs only
 int launch_carved_attn_v3(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                           const attn::KernelParams& p, unsigned grid, bool bf16, int split, cudaStream_t stream);
+// kernel generation 4 (carved_attn_v4.cu): 1 CTA/SM, two softmax streams (in-CTA split-KV), N=128 MMAs
+int launch_carved_attn_v4(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                          const attn::KernelParams& p, unsigned grid, bool bf16, cudaStream_t stream);
+// kernel generation 5 (carved_attn_v5.cu): generation 4 with two threads per query row
+int launch_carved_attn_v5(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                          const attn::KernelParams& p, unsigned grid, bool bf16, cudaStream_t stream);
 }  // namespace jenga

@@ -150,7 +150,7 @@ carved_attn_v3_kernel(const __grid_constant__ CUtensorMap tm_q,
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0 && elect_one()) {
       mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
       tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, static_cast<int>(q_row0), h, b);
       tma_load_4d(sQ + kHalfTileBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b);
@@ -177,7 +177,7 @@ carved_attn_v3_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
   } else if (warp == 1) {
     // =============================== tcgen05 issuer ===============================
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, /*b_mn_major=*/false, 128, kBlock);
       constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, /*b_mn_major=*/true, 128, kHeadDim);
       auto issue_qk = [&](int j) {  // S[j&1] = Q~ K(j)^T, A from TMEM
