@@ -545,14 +545,11 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
        a->sp_rows <= 0 || a->sp_heads_total != a->heads * a->sp_world || a->batch != 1 || a->out_dtype != a->dtype))
     return set_error(JENGA_E_INVALID, "bad Ulysses epilogue arguments");
 
-  // Kernel generation: v2 (default) or v3 via JENGA_ATTN_KERNEL (tuning switch, same results).
+  // Kernel generation: 2 (default) or the experimental generation 6 via JENGA_ATTN_KERNEL=v6
+  // (tuning switch, same results up to fp32 rounding; profiles/README.md has the comparison).
   static const int gen = [] {
     const char* e = std::getenv("JENGA_ATTN_KERNEL");
-    if (e && std::strcmp(e, "v3") == 0) return 3;      // 8 softmax warps
-    if (e && std::strcmp(e, "v3x4") == 0) return 34;   // 16 softmax warps
-    if (e && std::strcmp(e, "v4") == 0) return 4;      // two softmax streams, N=128 MMAs
-    if (e && std::strcmp(e, "v5") == 0) return 5;      // ... and two threads per row
-    return 2;
+    return (e && std::strcmp(e, "v6") == 0) ? 6 : 2;
   }();
   const int kv_box_rows = gen != 2 ? kBlock : kHalf;
   CUtensorMap tm_q, tm_k, tm_v;
@@ -598,15 +595,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
   if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");
-  if (gen == 5)
-    return launch_carved_attn_v5(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
-  if (gen == 4)
-    return launch_carved_attn_v4(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
-  if (gen != 2 && a->sp_world > 0)
-    return set_error(JENGA_E_UNSUPPORTED, "the Ulysses fused epilogue is not built for kernel generation 3");
-  if (gen != 2)
-    return launch_carved_attn_v3(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16,
-                                 gen == 34 ? 4 : 2, stream);
+  if (gen == 6)
+    return launch_carved_attn_v6(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
   auto kern = a->dtype == JENGA_BF16 ? carved_attn_fwd_kernel<true> : carved_attn_fwd_kernel<false>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(carved_attn)");

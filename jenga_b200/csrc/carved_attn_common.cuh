@@ -1,4 +1,4 @@
-// Shared between the carved-attention kernel generations (carved_attn.cu, carved_attn_v3.cu).
+// Shared between the carved-attention kernel generations (carved_attn.cu, carved_attn_v6.cu).
 #pragma once
 #include "sm100_ptx.cuh"
 #include "jenga_internal.h"
@@ -53,13 +53,7 @@ struct BlockWalker {
 
 }  // namespace attn
 
-// kernel generation 3 (carved_attn_v3.cu): 1 CTA/SM, Q in TMEM, N=128 MMAs only
-int launch_carved_attn_v3(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                          const attn::KernelParams& p, unsigned grid, bool bf16, int split, cudaStream_t stream);
-// kernel generation 4 (carved_attn_v4.cu): 1 CTA/SM, two softmax streams (in-CTA split-KV), N=128 MMAs
-int launch_carved_attn_v4(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                          const attn::KernelParams& p, unsigned grid, bool bf16, cudaStream_t stream);
-// kernel generation 5 (carved_attn_v5.cu): generation 4 with two threads per query row
-int launch_carved_attn_v5(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+// kernel generation 6 (carved_attn_v6.cu): three tiles in flight over one accumulator
+int launch_carved_attn_v6(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                           const attn::KernelParams& p, unsigned grid, bool bf16, cudaStream_t stream);
 }  // namespace jenga

@@ -4,6 +4,8 @@ Tolerance: bf16 max-abs <= 2e-2 and mean-abs <= 2e-3 relative t
 RMS; fp16 max-abs <= 5e-3 relative to the output RMS... stated per test below.
 """
 import math
+import sys
+from pathlib import Path
 
 import pytest
 import torch
@@ -131,3 +133,17 @@ def test_carved_attention_matches_reference_triton_golden(name):
     # rows at or past seqlen are exact zeros in both
     if c["seqlen"] < n_img * 128:
         assert (got[:, :, c["seqlen"]:] == 0).all() and (ref[:, :, c["seqlen"]:] == 0).all()
+
+
+def test_generation6_kernel_passes_the_same_parity_suite():
+    """JENGA_ATTN_KERNEL=v6 (experimental: three tiles in flight over one accumulator, stale shared
+    softmax reference) must satisfy exactly the same parity tests as the default generation.  The
+    switch is read once per process, so the suite is re-run in a child process."""
+    import os
+    import subprocess
+    env = dict(os.environ, JENGA_ATTN_KERNEL="v6")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-q", "-x", "-m", "gpu",
+                        "-k", "not generation6", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
