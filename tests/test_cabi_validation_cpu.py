@@ -70,6 +70,12 @@ def test_select_and_pool_validation():
     s.dtype, s.batch_heads, s.head_dim, s.nq, s.nk_pool, s.n_img, s.nb = 0, 1, 128, 4, 4, 4, 6
     s.mask_words = 0
     assert lib.jenga_select_blocks(C.byref(s), None) == E_INVALID and "mask_words" in _err()
+    # score workspace: size query, and a too-small workspace is refused before anything launches
+    assert lib.jenga_select_blocks_workspace_bytes(24, 900, 900) == 24 * 900 * 900 * 4
+    assert lib.jenga_select_blocks_workspace_bytes(0, 900, 900) == 0
+    s.mask_words, s.top_k, s.p_threshold = 1, 1, 0.5
+    s.workspace, s.workspace_bytes = 0x2000, 4 * 4 * 4 - 1
+    assert lib.jenga_select_blocks(C.byref(s), None) == -4 and "workspace" in _err()  # JENGA_E_WORKSPACE
     assert lib.jenga_block_pool(None, None, None, 0, 0, 1, 1, 128, 128, 0, 0, 0, 1, None) == E_INVALID
     # n_blocks beyond the rows
     assert lib.jenga_block_pool(0x1000, 0x1000, None, 0, 0, 1, 1, 128, 128, 16384, 128, 128, 2, None) == E_INVALID
