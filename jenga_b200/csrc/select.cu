@@ -145,7 +145,8 @@ struct SelectParams {
   int nbr_rows, nbr_words;
   uint32_t* out_bits;  // [BH, nq, words]
   int32_t* out_counts;  // [BH, nq] importance count n (before unions), may be null
-  int rows_per_cta;
+  int rows_per_cta;          // fused kernel: rows handled by one CTA
+  long long total_rows;      // two-kernel path: batch_heads * nq
   int npow2;  // sort width
 };
 
@@ -504,8 +505,7 @@ select_rows_kernel(const float* __restrict__ scores, const SelectParams p) {
   __shared__ uint32_t s_bits_all[4][64];  // up to 2048 key blocks per row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rowid = static_cast<long long>(blockIdx.x) * 4 + warp;  // (bh, m) flattened
-  const long long total_rows = p.rows_per_cta;  // (field reused: total number of rows)
-  if (rowid >= total_rows) return;
+  if (rowid >= p.total_rows) return;
   const int bh = static_cast<int>(rowid / p.nq);
   const int m = static_cast<int>(rowid - static_cast<long long>(bh) * p.nq);
   uint32_t* bits = s_bits_all[warp];
@@ -674,7 +674,7 @@ int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream) {
     p.out_bits = a->out_bits; p.out_counts = a->out_counts;
     const long long rows = static_cast<long long>(a->batch_heads) * a->nq;
     if (rows > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "select_blocks: too many rows");
-    p.rows_per_cta = static_cast<int>(rows);  // (reused field: total rows for select_rows_kernel)
+    p.total_rows = rows;
     select_rows_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, stream>>>(scores, p);
     ce = cudaGetLastError();
     return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "select_blocks (2-kernel) launch");
