@@ -20,6 +20,12 @@ imported by path and not edited):
       call it under torch.autocast("cuda", bfloat16) (pipeline_hunyuan_video_prores.py:663-665,
       jenga_wan.py:135) whose fp32 op list promotes softmax and cumsum; CPU autocast does not,
       so torch.softmax / torch.cumsum are wrapped to upcast to fp32 for the duration of the call.
+    - `block_sparse_attention` (the whole operator, hyvideo and hyvideo_i2v variants): the glue,
+      the mask builder and the Triton kernel run as above; the one third-party call on the path,
+      `flash_attn.flash_attn_func` for the text rows (:377), needs a GPU and is replaced by an
+      fp32 softmax attention on the same tensors (`_cpu_flash_attn_func`).  The wan variant casts
+      to bfloat16 internally (wan/…:456), which the interpreter cannot run, so it has no
+      operator-level fixture (its mask builder and prologue do).
 """
 import contextlib
 import hashlib
@@ -242,8 +248,44 @@ def wan_prologue_goldens():
     print("wan_prologue", out["q"].shape, flush=True)
 
 
+# ----------------------------------------------------------------------------- whole operator (a-11)
+def _cpu_flash_attn_func(q, k, v, causal=False, softmax_scale=None, **kw):
+    """Stand-in for the third-party FlashAttention-2 call (flash_attn.flash_attn_func, text rows,
+    …triton_diffres.py:377), which cannot run without a GPU: fp32 softmax attention on [B,S,H,D],
+    result in the input dtype.  Everything else in the call below is the unmodified reference."""
+    assert not causal
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * softmax_scale
+    return (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).to(q.dtype)
+
+
+def operator_goldens():
+    """reference block_sparse_attention (glue + mask builder + Triton kernel in the interpreter +
+    the FA2 stand-in above) on fp16 inputs: HunyuanVideo variant with cu_seqlens, I2V variant with
+    padding / trim / shape_xfuse."""
+    _patch_interpreter()
+    import synth
+    mods = {"hyvideo": _import("ref_hy_op", REF / "hyvideo/modules/attention_block_triton_diffres.py"),
+            "hyvideo_i2v": _import("ref_i2v_op", REF / "hyvideo_i2v/modules/attention_block_triton_diffres.py")}
+    out = {}
+    for name, *_ in synth.OPERATOR_CASES:
+        c = synth.operator_case(name)
+        m = mods[c["variant"]]
+        m.flash_attn_func = _cpu_flash_attn_func
+        with _cuda_autocast_dtype_flow():
+            o = m.block_sparse_attention(
+                c["q"], c["k"], c["v"], c["top_k"], cu_seqlens_q=c["cu"], cu_seqlens_kv=c["cu"],
+                text_blocks=c["text_blocks"], text_amp=c["amp"], block_neighbor_list=c["nbr"],
+                shape_xfuse=c["xfuse"], p_remain_rates=c["p"])
+        out[name + "/o"] = o.numpy()
+        print("operator", name, tuple(o.shape), float(o.float().abs().mean()), flush=True)
+    np.savez_compressed(OUT / "operator_fp16.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gilbert", "attention", "mask", "prologue", "wan_prologue"]
+    which = sys.argv[1:] or ["gilbert", "attention", "mask", "prologue", "wan_prologue", "operator"]
+    if "operator" in which:
+        operator_goldens()
     if "wan_prologue" in which:
         wan_prologue_goldens()
     if "prologue" in which:

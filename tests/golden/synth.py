@@ -149,3 +149,29 @@ def wan_prologue_case():
     # a fixed pseudo-random permutation standing in for hilbert_order
     remap = torch.from_numpy(np.argsort(_splitmix64(np.arange(n, dtype=np.uint64) + np.uint64(99)), kind="stable").astype(np.int64))
     return dict(L=L, H=c["H"], grid=c["grid"], xq=xq, xk=xk, wq=wq, wk=wk, remap=remap)
+
+
+OPERATOR_CASES = [
+    # name, variant, H, img_tokens, txt_tokens, txt_valid, top_k, p, text_amp, shape_xfuse, seed
+    ("hy_op", "hyvideo", 2, 6 * 128, 256, 150, 2, 0.3, 0.431, False, 61),
+    ("i2v_op", "hyvideo_i2v", 2, 5 * 128, 400, 300, 2, 0.3, 0.0, True, 62),
+]
+
+
+def operator_case(name):
+    """fp16 [B,S,H,D] inputs of one whole-operator call (reference block_sparse_attention)."""
+    for n, variant, H, L, T, t_valid, top_k, p, amp, xfuse, seed in OPERATOR_CASES:
+        if n != name:
+            continue
+        S = L + T
+        nbk = (S + 127) // 128
+        q = peaky(H, nbk, 128, 2.0, seed * 10)[:, :, :S].transpose(1, 2).contiguous().half()
+        k = peaky(H, nbk, 128, 2.0, seed * 10 + 3)[:, :, :S].transpose(1, 2).contiguous().half()
+        v = normal((1, S, H, 128), seed * 10 + 6).half()
+        cu = torch.tensor([0, L + t_valid, S], dtype=torch.int32)
+        text_blocks = 2 if variant == "hyvideo" else 4
+        n_img = (S + 127) // 128 - text_blocks
+        return dict(variant=variant, H=H, L=L, T=T, S=S, q=q, k=k, v=v, cu=cu, top_k=top_k, p=p,
+                    amp=amp, xfuse=xfuse, text_blocks=text_blocks, n_img=n_img,
+                    nbr=band_neighbours(n_img))
+    raise KeyError(name)

@@ -79,3 +79,24 @@ def test_shape_xfuse_and_no_text():
     o = block_sparse_attention_variant("wan", q.to(dev), k.to(dev), v.to(dev), shape_xfuse=True,
                                        block_neighbor_list=nbr, **kw)
     assert o.shape == q.shape and torch.isfinite(o).all()
+
+
+@pytest.mark.parametrize("name", [n for n, *_ in synth.OPERATOR_CASES])
+def test_operator_matches_reference_golden(name):
+    """Product (through the C-ABI) against the output of the UNMODIFIED reference operator on the
+    same fp16 inputs (tests/golden/operator_fp16.npz; Triton kernel run in the interpreter, the
+    FlashAttention-2 text-row call replaced by fp32 attention — see make_golden.py).  Tolerance:
+    the fp16 attention bound of test_attn_gpu.assert_close."""
+    import numpy as np
+    from jenga_b200.attention import block_sparse_attention_variant
+    gold = np.load(HERE / "golden" / "operator_fp16.npz")
+    c = synth.operator_case(name)
+    dev = "cuda"
+    out = block_sparse_attention_variant(
+        c["variant"], c["q"].to(dev), c["k"].to(dev), c["v"].to(dev), top_k=c["top_k"],
+        cu_seqlens_q=c["cu"].to(dev), cu_seqlens_kv=c["cu"].to(dev), text_blocks=c["text_blocks"],
+        text_amp=c["amp"], block_neighbor_list=c["nbr"], shape_xfuse=c["xfuse"], p_remain_rates=c["p"])
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(gold[name + "/o"])
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    assert_close(out.cpu(), ref, torch.float16)

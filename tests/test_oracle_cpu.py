@@ -40,6 +40,29 @@ def test_attention_oracle_matches_reference_triton(name):
     assert (got[:, :, c["seqlen"]:] == 0).all()
 
 
+# ------------------------------------------------------------------ whole-operator oracle vs reference
+@pytest.mark.parametrize("name", [n for n, *_ in synth.OPERATOR_CASES])
+def test_operator_oracle_matches_reference_block_sparse_attention(name):
+    """oracle.block_sparse_attention against the output of the reference's own
+    block_sparse_attention (glue + mask builder + Triton kernel + text rows; fixture made by
+    tests/golden/make_golden.py operator): layout ([B,S,H*D] vs shape_xfuse), cu_seqlens handling,
+    I2V padding/trim and the selection all have to agree for the values to agree."""
+    gold = np.load(HERE / "golden" / "operator_fp16.npz")
+    c = synth.operator_case(name)
+    ref = torch.from_numpy(gold[name + "/o"])
+    got = orc.block_sparse_attention(
+        c["q"], c["k"], c["v"], c["top_k"], cu_seqlens_q=c["cu"], cu_seqlens_kv=c["cu"],
+        text_blocks=c["text_blocks"], text_amp=c["amp"], block_neighbor_list=c["nbr"],
+        shape_xfuse=c["xfuse"], p_remain_rates=c["p"],
+        variant="i2v" if c["variant"] == "hyvideo_i2v" else "hyvideo")
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    ref, got = ref.float(), got.float()
+    rms = ref.pow(2).mean().sqrt()
+    d = (got - ref).abs()
+    assert d.max() <= 5e-3 * rms + 2.0 ** -10 * ref.abs().max(), (d.max() / rms).item()
+    assert d.mean() <= 2e-4 * rms, (d.mean() / rms).item()
+
+
 # ------------------------------------------------------------------ mask-builder oracle vs torch
 def assert_masks_equal_modulo_ties(got, ref, probs, n_img):
     """Selection parity contract: identical masks, except that inside ONE group
