@@ -92,3 +92,53 @@ def test_gilbert_host_entry_points_validate_and_run():
     assert sorted(a.tolist()) == list(range(8))
     assert lib.jenga_gilbert_xyz2d(5, 0, 0, 4, 4, 4) == -1  # out of bounds
     assert lib.jenga_gilbert_block_neighbors_host(1, 2, 4, 0, 0, a.ctypes.data) == E_INVALID
+
+
+def _hy_args(**over):
+    from jenga_b200._lib import JengaHyPrologueArgs
+    a = JengaHyPrologueArgs()
+    a.img_qkv = a.txt_qkv = a.q = a.k = a.v = 0x10000
+    a.dtype, a.batch, a.heads, a.head_dim = _lib.JENGA_BF16, 1, 2, 128
+    a.img_tokens, a.txt_tokens = 256, 64
+    a.img_stride_b, a.img_stride_s, a.img_stride_w, a.img_stride_h = 256 * 768, 768, 256, 128
+    a.txt_stride_b, a.txt_stride_s, a.txt_stride_w, a.txt_stride_h = 64 * 768, 768, 256, 128
+    a.eps = 1e-6
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize("over,code,needle", [
+    (dict(q=None), E_INVALID, "null"),
+    (dict(dtype=_lib.JENGA_F32), E_INVALID, "dtype"),
+    (dict(head_dim=64), E_UNSUPPORTED, "head_dim"),
+    (dict(img_tokens=0), E_INVALID, "shape"),
+    (dict(txt_qkv=None), E_INVALID, "txt_qkv"),
+    (dict(w_img_q=0x2000), E_INVALID, "norm weights"),
+    (dict(rope_cos=0x2000), E_INVALID, "cos and sin"),
+    (dict(q_pool=0x2000), E_INVALID, "q_pool"),
+    (dict(img_stride_s=770), E_INVALID, "strides"),
+])
+def test_hy_prologue_argument_validation(over, code, needle):
+    """jenga_hy_prologue (RMSNorm+RoPE+cat+pool) rejects bad arguments before any launch."""
+    assert lib.jenga_hy_prologue(C.byref(_hy_args(**over)), None) == code
+    assert needle in _err()
+
+
+def test_wan_prologue_and_ulysses_scatter_validation():
+    from jenga_b200._lib import JengaUlyssesScatterArgs, JengaWanPrologueArgs
+    w = JengaWanPrologueArgs()
+    assert lib.jenga_wan_prologue(C.byref(w), None) == E_INVALID and "null" in _err()
+    w.x = w.out = 0x10000
+    w.batch, w.heads, w.head_dim, w.tokens = 1, 12, 64, 128
+    assert lib.jenga_wan_prologue(C.byref(w), None) == E_UNSUPPORTED and "head_dim" in _err()
+    w.head_dim, w.tokens = 128, 0
+    assert lib.jenga_wan_prologue(C.byref(w), None) == E_INVALID and "shape" in _err()
+    w.tokens, w.x_dtype = 128, _lib.JENGA_F16
+    assert lib.jenga_wan_prologue(C.byref(w), None) == E_INVALID and "dtypes" in _err()
+    w.x_dtype, w.w_dtype = _lib.JENGA_F32, _lib.JENGA_BF16
+    w.freqs, w.freq_rows, w.grid_f, w.grid_h, w.grid_w = 0x2000, 8, 21, 30, 52   # needs >= 52 rows
+    assert lib.jenga_wan_prologue(C.byref(w), None) == E_INVALID and "frequency table" in _err()
+
+    s = JengaUlyssesScatterArgs()
+    assert lib.jenga_ulysses_scatter(C.byref(s), None) == E_INVALID and "null" in _err()
