@@ -303,3 +303,20 @@ def test_install_launcher_runs_a_script_with_the_hook(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "HOOK [0, 1, 26, 25]" in r.stdout and "jenga_b200 drop-in (hyvideo variant)" in r.stdout
     assert "['--video-size', '720']" in r.stdout
+
+
+def test_host_block_count_rules_match_reference_arithmetic():
+    """a-7: the top_k / first-frame rules are plain host arithmetic with float
+    truncation quirks — models_mul…:242,249-251 and wan/modules/model_mul.py:161-164."""
+    from jenga_b200 import wan
+    from jenga_b200.hyvideo import select_block_num
+    assert select_block_num(0.7, 115200) == 270
+    assert select_block_num(0.75, 115200) == 225
+    assert select_block_num(0.8, 115200) == 179        # int(0.2 * 900) = 179: 0.19999999999999996 * 900
+    assert select_block_num(0.85, 115200) == 135
+    assert select_block_num(0.75, 63360) == 123        # Turbo stage 0, single GPU
+    assert select_block_num(0.75, 7920, world_size=8) == 120   # SP: 8 * int(0.25 * 61)
+    assert select_block_num(0.85, 14400, world_size=8) == 128  # SP: 8 * int(0.15 * 112)
+    assert wan.block_counts(32760, 0.5) == (128, 12)   # Wan-1.3B: 256 blocks
+    assert wan.block_counts(75600, 0.7) == (177, 28)   # Wan-14B: 591 blocks
+    assert wan.block_counts(75600, 0.8) == (118, 28)
