@@ -254,6 +254,83 @@ def cpu_sample(wl, kind: str, budget_s: float = 12.0):
 
 
 # ------------------------------------------------------------------------------------------------
+# GPU reference leg: the UNMODIFIED reference operator (Triton JIT + FlashAttention-2) on the same
+# tensors on the same B200 (SURVEY §8d "Reference timed beside it (1)").  Checker/baseline only.
+# ------------------------------------------------------------------------------------------------
+def gpu_reference_leg(wl, inp, iters=3):
+    sys.path.insert(0, str(ROOT / "tests"))
+    try:
+        from oracle import ref_loader
+        import refutil
+        if not ref_loader.available():
+            return {"unavailable": "oracle/_ref/ not staged (run __graft_entry__.build() where /root/reference is mounted)"}
+        op = ref_loader.operator(wl["variant"])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    q, k, v, cu, nbr = inp["q"], inp["k"], inp["v"], inp["cu"], inp["nbr"]
+    S = inp["S"]
+    nb = (S + BLOCK - 1) // BLOCK
+    tb = wl["text_blocks"]
+    n_img = nb - tb
+    kw = dict(top_k=inp["top_k"], text_blocks=tb, nbr=nbr, p_remain=wl["p_remain"], first_frame=wl["first_frame"])
+    nbr_dev = nbr.to(q.device)  # the reference moves it lazily on first use (:282-283); keep that out of the timing
+    kw["nbr"] = nbr_dev
+
+    def total():
+        return refutil.reference_call(op, wl["variant"], q, k, v, cu=cu, text_amp=wl["text_amp"], **kw)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    try:
+        for _ in range(3):  # first call includes the Triton JIT
+            total()
+        total_ms, _ = timed(total, iters)
+        mask_ms, mask = timed(lambda: refutil.reference_mask(op, wl["variant"], q, k, **kw), iters)
+        # the two kernels alone, on the layouts block_sparse_attention_combined hands them
+        qh, kh, vh = (refutil.pad_rows(x, nb * BLOCK).transpose(1, 2) for x in (q, k, v))
+        if wl["variant"] == "wan":
+            qh, kh, vh = (x.to(torch.bfloat16) for x in (qh, kh, vh))
+        seq = (cu[1:2].to(torch.int32) if (cu is not None and wl["variant"] != "wan")
+               else torch.tensor([S], dtype=torch.int32, device=q.device))
+        triton_ms, _ = timed(lambda: op._triton_block_sparse_attention_onehot(
+            qh[:, :, :n_img * BLOCK], kh, vh, seq, mask, 128 ** -0.5, BLOCK, BLOCK, is_text_block=False,
+            text_amp=wl["text_amp"], text_block_start=n_img), iters)
+        fa2_ms = None
+        if tb > 0:
+            fa2_ms, _ = timed(lambda: op.flash_attn_func(
+                qh[:, :, n_img * BLOCK:].permute(0, 2, 1, 3), kh.permute(0, 2, 1, 3), vh.permute(0, 2, 1, 3),
+                causal=False, softmax_scale=128 ** -0.5), iters)
+        pop = int(mask.sum().item())
+        flops = pop * 4 * BLOCK * BLOCK * 128 + 4 * inp["heads"] * tb * BLOCK * nb * BLOCK * 128
+        isa = None
+        try:
+            kern = op._triton_block_sparse_attn_fwd_kernel_onehot
+            for cache in getattr(kern, "device_caches", {}).values():
+                for ck in cache[0].values():
+                    ptx = ck.asm.get("ptx", "")
+                    isa = {"tcgen05.mma": ptx.count("tcgen05.mma"), "mma.sync": ptx.count("mma.sync"),
+                           "wgmma": ptx.count("wgmma"), "cp.async.bulk": ptx.count("cp.async.bulk")}
+        except Exception:  # noqa: BLE001
+            pass
+        return {"impl": "unmodified reference block_sparse_attention (Triton %s JIT + flash_attn %s)" % (
+                    __import__("triton").__version__, __import__("flash_attn").__version__),
+                "total_ms": total_ms, "mask_ms": mask_ms, "triton_ms": triton_ms, "fa2_ms": fa2_ms,
+                "live_tiles": pop, "tflops": flops / (total_ms * 1e-3) / 1e12,
+                "triton_kernel_tflops": pop * 4 * BLOCK * BLOCK * 128 / (triton_ms * 1e-3) / 1e12,
+                "triton_ptx_mma": isa, "iters": iters, "autocast": "bf16"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +345,8 @@ def main():
                          "(23 = the whole 50-step video: 1380 hot-path calls) and report measured "
                          "hot-path seconds per video")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip timing the unmodified reference operator (Triton + FA2) on this GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = workload(args.workload, args.drop)
@@ -493,6 +572,12 @@ def main():
         cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
                "sample": "oracle/attention_oracle.carved_attention_rows: " + sample}
 
+    gref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        gref = gpu_reference_leg(wl, inp)
+        if "total_ms" in gref:
+            gref["speedup_of_this_operator"] = gref["total_ms"] / ms
+
     if rank == 0:
         value = flops / (ms * 1e-3) / 1e12
         launches = 4 if world == 1 else 4  # block_pool x2, select_blocks, carved_attn per step
@@ -516,6 +601,9 @@ def main():
             line["cpu_baseline"] = cpu
         if dit:
             line["dit_loop"] = dit
+        if gref:
+            line["gpu_reference"] = gref
+            line["vs_gpu_reference"] = gref.get("speedup_of_this_operator")
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -53,7 +53,18 @@ int jenga_gilbert_mapping_host(int t, int h, int w, int sliced, int64_t* linear_
                                int64_t* hilbert_to_linear);
 int jenga_gilbert_block_neighbors_host(int t, int h, int w, int block, int sliced,
                                        uint8_t* neighbors /* [nb*nb] */);
-/* Scalar curve index of one voxel.  ref: gilbert.py:12 gilbert_xyz2d. */
+/* Adjacency of the blocks of ANY voxel->curve-index table (e.g. a transposed curve,
+ * gilbert.py:274 transpose_gilbert_mapping, which the sliced adjacency builder accepts at :704). */
+int jenga_block_neighbors_from_mapping_host(int t, int h, int w, int block,
+                                            const int64_t* linear_to_hilbert,
+                                            uint8_t* neighbors /* [nb*nb] */);
+/* The same adjacency as CSR: row_ptr[nb+1], col_idx[nnz] ascending per row.
+ * Call with col_idx == NULL to size (nnz_out), then with capacity >= nnz. */
+int jenga_gilbert_block_neighbors_csr_host(int t, int h, int w, int block, int sliced,
+                                           int32_t* row_ptr, int32_t* col_idx,
+                                           int64_t col_capacity, int64_t* nnz_out);
+/* Scalar curve index of one voxel.  ref: gilbert.py:12 gilbert_xyz2d.  The table of the last
+ * queried box is cached per thread, so a loop over a box costs one walk. */
 int64_t jenga_gilbert_xyz2d(int x, int y, int z, int width, int height, int depth);
 
 /* ------------------------------------------------------------------------------------------

@@ -131,6 +131,12 @@ def _load() -> C.CDLL:
     lib.jenga_copy2d_async.restype = C.c_int
     lib.jenga_ulysses_scatter.argtypes = [C.POINTER(JengaUlyssesScatterArgs), C.c_void_p]
     lib.jenga_ulysses_scatter.restype = C.c_int
+    lib.jenga_block_neighbors_from_mapping_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int,
+                                                            C.c_void_p, C.c_void_p]
+    lib.jenga_block_neighbors_from_mapping_host.restype = C.c_int
+    lib.jenga_gilbert_block_neighbors_csr_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.jenga_gilbert_block_neighbors_csr_host.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 1:

@@ -8,6 +8,7 @@ torch is used for device memory and the current stream only.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -147,13 +148,15 @@ def neighbour_bits(block_neighbor_list: torch.Tensor, device) -> torch.Tensor:
     key = (block_neighbor_list.data_ptr(), tuple(block_neighbor_list.shape),
            block_neighbor_list._version, str(device))
     hit = _NBR_CACHE.get(key)
-    if hit is not None:
-        return hit
+    # the entry remembers WHICH tensor it was packed from: a freed adjacency whose address is
+    # reused by another curve's matrix of the same shape must not hit
+    if hit is not None and hit[0]() is block_neighbor_list:
+        return hit[1]
     m = block_neighbor_list.to(device=device, dtype=torch.bool)
     bits = mask_onehot_to_bits(m)
     if len(_NBR_CACHE) > 64:
         _NBR_CACHE.clear()
-    _NBR_CACHE[key] = bits
+    _NBR_CACHE[key] = (weakref.ref(block_neighbor_list), bits)
     return bits
 
 
@@ -254,10 +257,14 @@ def block_sparse_attention_variant(
         def to_bf16_with_pool(x, want_pool, n_pool):
             if x.dtype == torch.bfloat16:
                 return x, (block_pool(x, n_pool) if want_pool and n_pool > 0 else None)
+            # the cast must cover EVERY row (wan/…:456-463 casts the whole padded tensor), so the
+            # kernel runs over all nb blocks; only the first n_pool pooled rows are ranked
             xf = x if x.dtype == torch.float32 else x.float()
             xc = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            pooled = block_pool(xf, max(n_pool, 1), cast_out=xc)
-            return xc, (pooled if want_pool and n_pool > 0 else None)
+            pooled = block_pool(xf, nb, cast_out=xc)
+            if not (want_pool and n_pool > 0):
+                return xc, None
+            return xc, (pooled if n_pool == nb else pooled[:, :, :n_pool].contiguous())
         q, q_pool = to_bf16_with_pool(q, True, normal_blocks)
         k, k_pool = to_bf16_with_pool(k, True, normal_blocks)
         v, _ = to_bf16_with_pool(v, False, 0) if v.dtype != torch.bfloat16 else (v, None)

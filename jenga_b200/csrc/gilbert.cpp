@@ -149,13 +149,20 @@ int build_mapping(int t, int h, int w, int sliced, int64_t* l2h, int64_t* h2l) {
 
 extern "C" int64_t jenga_gilbert_xyz2d(int x, int y, int z, int width, int height, int depth) {
   if (x < 0 || y < 0 || z < 0 || x >= width || y >= height || z >= depth) return -1;
-  std::vector<int64_t> l2h(static_cast<size_t>(width) * height * depth);
-  Walker wk;
-  wk.W = width;
-  wk.H = height;
-  wk.to_curve = l2h.data();
-  wk.run(width, height, depth);
-  return l2h[(static_cast<size_t>(z) * height + y) * width + x];
+  // The reference answers one voxel per call (gilbert.py:12-38); callers loop over a whole box,
+  // so the table of the last box is kept (per thread) and a query is one load.
+  thread_local int cw = 0, ch = 0, cd = 0;
+  thread_local std::vector<int64_t> table;
+  if (cw != width || ch != height || cd != depth) {
+    table.assign(static_cast<size_t>(width) * height * depth, 0);
+    Walker wk;
+    wk.W = width;
+    wk.H = height;
+    wk.to_curve = table.data();
+    wk.run(width, height, depth);
+    cw = width, ch = height, cd = depth;
+  }
+  return table[(static_cast<size_t>(z) * height + y) * width + x];
 }
 
 extern "C" int jenga_gilbert_mapping_host(int t, int h, int w, int sliced,
@@ -165,18 +172,19 @@ extern "C" int jenga_gilbert_mapping_host(int t, int h, int w, int sliced,
   return build_mapping(t, h, w, sliced, linear_to_hilbert, hilbert_to_linear);
 }
 
-extern "C" int jenga_gilbert_block_neighbors_host(int t, int h, int w, int block, int sliced,
-                                                  uint8_t* neighbors) {
-  if (!neighbors || block <= 0) return jenga::set_error(JENGA_E_INVALID, "gilbert: bad argument");
+namespace {
+
+// 26-neighbourhood + self over the voxel grid for ANY voxel->curve-index table
+// (gilbert.py:633-663 / :727-757: both builders colour voxels by idx // block and union).
+int neighbours_from_table(int t, int h, int w, int block, const int64_t* l2h, uint8_t* neighbors) {
   const int64_t n = static_cast<int64_t>(t) * h * w;
-  if (n <= 0) return jenga::set_error(JENGA_E_INVALID, "gilbert: empty grid");
-  std::vector<int64_t> l2h(n);
-  if (int rc = build_mapping(t, h, w, sliced, l2h.data(), nullptr)) return rc;
   const int64_t nb = (n + block - 1) / block;
   std::vector<int32_t> colour(n);
-  for (int64_t i = 0; i < n; ++i) colour[i] = static_cast<int32_t>(l2h[i] / block);
+  for (int64_t i = 0; i < n; ++i) {
+    if (l2h[i] < 0 || l2h[i] >= n) return jenga::set_error(JENGA_E_INVALID, "gilbert: table entry out of range");
+    colour[i] = static_cast<int32_t>(l2h[i] / block);
+  }
   for (int64_t i = 0; i < nb * nb; ++i) neighbors[i] = 0;
-  // 26-neighbourhood + self over the voxel grid (gilbert.py:633-663)
   for (int z = 0; z < t; ++z)
     for (int y = 0; y < h; ++y)
       for (int x = 0; x < w; ++x) {
@@ -196,5 +204,50 @@ extern "C" int jenga_gilbert_block_neighbors_host(int t, int h, int w, int block
           }
         }
       }
+  return JENGA_OK;
+}
+
+}  // namespace
+
+extern "C" int jenga_gilbert_block_neighbors_host(int t, int h, int w, int block, int sliced,
+                                                  uint8_t* neighbors) {
+  if (!neighbors || block <= 0) return jenga::set_error(JENGA_E_INVALID, "gilbert: bad argument");
+  const int64_t n = static_cast<int64_t>(t) * h * w;
+  if (n <= 0) return jenga::set_error(JENGA_E_INVALID, "gilbert: empty grid");
+  std::vector<int64_t> l2h(n);
+  if (int rc = build_mapping(t, h, w, sliced, l2h.data(), nullptr)) return rc;
+  return neighbours_from_table(t, h, w, block, l2h.data(), neighbors);
+}
+
+extern "C" int jenga_block_neighbors_from_mapping_host(int t, int h, int w, int block,
+                                                       const int64_t* linear_to_hilbert,
+                                                       uint8_t* neighbors) {
+  if (!neighbors || !linear_to_hilbert || block <= 0 || t <= 0 || h <= 0 || w <= 0)
+    return jenga::set_error(JENGA_E_INVALID, "gilbert: bad argument");
+  return neighbours_from_table(t, h, w, block, linear_to_hilbert, neighbors);
+}
+
+extern "C" int jenga_gilbert_block_neighbors_csr_host(int t, int h, int w, int block, int sliced,
+                                                      int32_t* row_ptr, int32_t* col_idx,
+                                                      int64_t col_capacity, int64_t* nnz_out) {
+  if (!row_ptr || block <= 0) return jenga::set_error(JENGA_E_INVALID, "gilbert: bad argument");
+  const int64_t n = static_cast<int64_t>(t) * h * w;
+  if (n <= 0) return jenga::set_error(JENGA_E_INVALID, "gilbert: empty grid");
+  const int64_t nb = (n + block - 1) / block;
+  std::vector<uint8_t> dense(static_cast<size_t>(nb) * nb);
+  if (int rc = jenga_gilbert_block_neighbors_host(t, h, w, block, sliced, dense.data())) return rc;
+  int64_t nnz = 0;
+  for (int64_t i = 0; i < nb; ++i) {
+    row_ptr[i] = static_cast<int32_t>(nnz);
+    for (int64_t j = 0; j < nb; ++j)
+      if (dense[i * nb + j]) {
+        if (col_idx && nnz < col_capacity) col_idx[nnz] = static_cast<int32_t>(j);
+        ++nnz;
+      }
+  }
+  row_ptr[nb] = static_cast<int32_t>(nnz);
+  if (nnz_out) *nnz_out = nnz;
+  if (col_idx && nnz > col_capacity)
+    return jenga::set_error(JENGA_E_INVALID, "gilbert: col_idx capacity too small (nnz returned)");
   return JENGA_OK;
 }

@@ -4,9 +4,12 @@ Same names, arguments and return types as gilbert.py:442 gilbert_mapping, :332
 sliced_gilbert_mapping, :597 gilbert_block_neighbor_mapping and :679
 sliced_gilbert_block_neighbor_mapping (lists of Python ints / a bool torch tensor), computed by
 the O(N) curve walker in libjenga_b200.so (csrc/gilbert.cpp) instead of one recursive Python
-call per voxel.  `transpose_order` (never passed by the reference's scripts) is not built.
+call per voxel.  `transpose_gilbert_mapping` / `transpose_order` (gilbert.py:274) are axis
+permutations of the walker's table.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
@@ -38,9 +41,31 @@ def block_neighbor_mapping(t: int, h: int, w: int, block_size: int = 128, sliced
     return torch.from_numpy(out).bool()
 
 
-def _no_transpose(transpose_order):
-    if transpose_order is not None:
-        raise NotImplementedError("transpose_order is not used by any Jenga script and is not built")
+def _check_order(order):
+    order = [0, 1, 2] if order is None else [int(o) for o in order]
+    if len(order) != 3 or set(order) != {0, 1, 2}:
+        raise ValueError("order must be a permutation of 0,1,2")   # gilbert.py:294-295
+    return order
+
+
+def _transposed_np(dims, order):
+    """gilbert.py:274-330: the curve is drawn in the box dims[order] and voxel `coords` of the
+    original box reads the index at coords[order]."""
+    if len(dims) != 3:
+        raise ValueError("Dimensions must be three-dimensional")       # gilbert.py:287-288
+    order = _check_order(order)
+    tt, hh, ww = (int(dims[o]) for o in order)
+    l2h_t, _ = _mapping_np(tt, hh, ww, False)
+    inv = np.argsort(order)
+    l2h = np.ascontiguousarray(l2h_t.reshape(tt, hh, ww).transpose(inv)).reshape(-1)
+    h2l = np.empty_like(l2h)
+    h2l[l2h] = np.arange(l2h.size, dtype=np.int64)
+    return l2h, h2l
+
+
+def transpose_gilbert_mapping(dims, order=None):
+    l2h, h2l = _transposed_np(dims, order)
+    return l2h.tolist(), h2l.tolist()
 
 
 def gilbert_xyz2d(x, y, z, width, height, depth):
@@ -48,22 +73,59 @@ def gilbert_xyz2d(x, y, z, width, height, depth):
 
 
 def gilbert_mapping(t, h, w, transpose_order=None):
-    _no_transpose(transpose_order)
+    if transpose_order is not None:
+        return transpose_gilbert_mapping([t, h, w], transpose_order)    # gilbert.py:484-486
     l2h, h2l = _mapping_np(t, h, w, False)
     return l2h.tolist(), h2l.tolist()
 
 
 def sliced_gilbert_mapping(t, h, w, transpose_order=None):
-    _no_transpose(transpose_order)
+    if transpose_order is not None:
+        return transpose_gilbert_mapping([t, h, w], transpose_order)    # gilbert.py:436-438
     l2h, h2l = _mapping_np(t, h, w, True)
     return l2h.tolist(), h2l.tolist()
 
 
 def gilbert_block_neighbor_mapping(t, h, w, block_size=128, transpose_order=None):
-    _no_transpose(transpose_order)
+    # the reference accepts transpose_order here and never reads it (gilbert.py:597-677)
     return block_neighbor_mapping(t, h, w, block_size, False)
 
 
 def sliced_gilbert_block_neighbor_mapping(t, h, w, block_size=128, transpose_order=None):
-    _no_transpose(transpose_order)
-    return block_neighbor_mapping(t, h, w, block_size, True)
+    if transpose_order is None:
+        return block_neighbor_mapping(t, h, w, block_size, True)
+    l2h, _ = _transposed_np([t, h, w], transpose_order)                 # gilbert.py:704
+    n = t * h * w
+    nb = (n + block_size - 1) // block_size
+    out = np.empty((nb, nb), dtype=np.uint8)
+    check(lib.jenga_block_neighbors_from_mapping_host(t, h, w, block_size, l2h.ctypes.data, out.ctypes.data),
+          "block_neighbors_from_mapping")
+    return torch.from_numpy(out).bool()
+
+
+def block_neighbor_csr(t: int, h: int, w: int, block_size: int = 128, sliced: bool = False):
+    """The adjacency as CSR (row_ptr int32 [nb+1], col_idx int32 [nnz]) — SURVEY §8 f-4."""
+    n = t * h * w
+    nb = (n + block_size - 1) // block_size
+    row_ptr = np.empty(nb + 1, dtype=np.int32)
+    nnz = C.c_int64(0)
+    check(lib.jenga_gilbert_block_neighbors_csr_host(t, h, w, block_size, int(sliced), row_ptr.ctypes.data,
+                                                     None, 0, C.byref(nnz)), "block_neighbors_csr")
+    col = np.empty(nnz.value, dtype=np.int32)
+    check(lib.jenga_gilbert_block_neighbors_csr_host(t, h, w, block_size, int(sliced), row_ptr.ctypes.data,
+                                                     col.ctypes.data, nnz.value, C.byref(nnz)),
+          "block_neighbors_csr")
+    return torch.from_numpy(row_ptr), torch.from_numpy(col)
+
+
+def _not_on_the_hot_path(name):
+    def f(*a, **k):
+        raise NotImplementedError(f"gilbert.{name} is a plotting/experiment helper no Jenga script calls")
+    f.__name__ = name
+    return f
+
+
+# imported by name in no script, defined so that `from gilbert import *`-style uses fail at CALL time
+block_wise_mapping = _not_on_the_hot_path("block_wise_mapping")
+visualize_gilbert_curve = _not_on_the_hot_path("visualize_gilbert_curve")
+visualize_gilbert_curves_comparison = _not_on_the_hot_path("visualize_gilbert_curves_comparison")

@@ -248,6 +248,33 @@ def wan_prologue_goldens():
     print("wan_prologue", out["q"].shape, flush=True)
 
 
+def gilbert_transpose_goldens():
+    """transpose_gilbert_mapping (gilbert.py:274) and the transpose_order arguments of the four
+    table builders, from the unmodified reference."""
+    for m in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    ref = _import("ref_gilbert", REF / "gilbert.py")
+    cases = {}
+    for dims, order in (([3, 4, 6], [2, 1, 0]), ([4, 6, 8], [1, 0, 2]), ([5, 3, 7], [0, 2, 1]),
+                        ([2, 5, 4], [1, 2, 0]), ([6, 9, 10], [2, 0, 1]), ([4, 4, 4], None)):
+        t, h, w = dims
+        with contextlib.redirect_stdout(io.StringIO()):
+            l2h, h2l = ref.transpose_gilbert_mapping(dims, order)
+            g = ref.gilbert_mapping(t, h, w, order)
+            sl = ref.sliced_gilbert_mapping(t, h, w, order)
+            nbr = ref.gilbert_block_neighbor_mapping(t, h, w, 16, order)
+            snbr = ref.sliced_gilbert_block_neighbor_mapping(t, h, w, 16, order)
+        key = "x".join(map(str, dims)) + "_" + ("none" if order is None else "".join(map(str, order)))
+        cases[key] = dict(dims=dims, order=order, l2h=[int(i) for i in l2h], h2l=[int(i) for i in h2l],
+                          gilbert_mapping_l2h_sha=sha16(np.asarray(g[0], dtype=np.int64)),
+                          sliced_mapping_l2h_sha=sha16(np.asarray(sl[0], dtype=np.int64)),
+                          nbr16_sha=sha16(nbr.numpy().astype(np.bool_)),
+                          sliced_nbr16_sha=sha16(snbr.numpy().astype(np.bool_)))
+        print("gilbert transpose", key, cases[key]["nbr16_sha"], flush=True)
+    (OUT / "gilbert_transpose.json").write_text(json.dumps(cases))
+
+
 # ----------------------------------------------------------------------------- whole operator (a-11)
 def _cpu_flash_attn_func(q, k, v, causal=False, softmax_scale=None, **kw):
     """Stand-in for the third-party FlashAttention-2 call (flash_attn.flash_attn_func, text rows,
@@ -283,7 +310,9 @@ def operator_goldens():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gilbert", "attention", "mask", "prologue", "wan_prologue", "operator"]
+    which = sys.argv[1:] or ["gilbert", "gilbert_transpose", "attention", "mask", "prologue", "wan_prologue", "operator"]
+    if "gilbert_transpose" in which:
+        gilbert_transpose_goldens()
     if "operator" in which:
         operator_goldens()
     if "wan_prologue" in which:
