@@ -140,6 +140,9 @@ def block_pool(x: torch.Tensor, n_blocks: int, cast_out: torch.Tensor | None = N
 
 
 _NBR_CACHE: dict = {}
+# tests set this to a list to record every selection result (bit rows, nb) of calls made deep
+# inside a block forward; None (the default) costs nothing
+MASK_CAPTURE: list | None = None
 
 
 def neighbour_bits(block_neighbor_list: torch.Tensor, device) -> torch.Tensor:
@@ -194,6 +197,8 @@ def select_blocks(q_pool: torch.Tensor, k_pool: torch.Tensor, *, n_img: int, nb:
         a.workspace, a.workspace_bytes = None, 0
     with torch.cuda.device(q_pool.device):
         check(lib.jenga_select_blocks(C.byref(a), _stream_ptr(q_pool.device)), "select_blocks")
+    if MASK_CAPTURE is not None:
+        MASK_CAPTURE.append((bits, nb))
     return (bits, counts) if return_counts else bits
 
 

@@ -27,8 +27,12 @@ def _module(name: str, **attrs) -> types.ModuleType:
     return m
 
 
-def install(flash_attn: bool = True, gilbert: bool = True, ulysses: bool = True) -> list[str]:
-    """Pre-seeds sys.modules; returns the names it installed."""
+def install(flash_attn: bool = True, gilbert: bool = True, ulysses: bool = True, fused_blocks: bool = True,
+            gather: bool = True) -> list[str]:
+    """Pre-seeds sys.modules; returns the names it installed.
+    fused_blocks: also patch the reference block classes right after they are imported so that
+    RMSNorm + RoPE + cat + pooling run as the fused prologue kernel (jenga_b200/blocks.py).
+    gather: route the token reorder `x[:, hilbert_order]` to the gather kernel."""
     from . import attention as A
     from . import flash_attn_shim as F
     from . import gilbert as G
@@ -56,12 +60,43 @@ def install(flash_attn: bool = True, gilbert: bool = True, ulysses: bool = True)
                                        block_sparse_attention_combined=fn)
         done.append(modname)
     if ulysses:
-        class xFuserLongContextAttention(U.UlyssesCarvedAttention):
-            """Same constructor surface as the reference class (all arguments ignored: ring
-            degree is 1 in every Jenga script) and the same forward contract."""
+        import os
+
+        class xFuserLongContextAttention:
+            """Same constructor surface as the reference class (all arguments ignored: ring degree
+            is 1 in every Jenga script, xdit_ring_atten.py:24-59) and the same forward contract.
+            The exchange runs fused over NVLink peer memory (UlyssesFusedAttention); if symmetric
+            memory cannot be set up on this box — or JENGA_ULYSSES=nccl — all ranks agree on the
+            NCCL all-to-all implementation.  Both are GPU paths of this library."""
+            _impl = None
+
             def __init__(self, *a, **k):
-                super().__init__(group=None)
-            forward = U.UlyssesCarvedAttention.__call__
+                pass
+
+            @classmethod
+            def _get(cls):
+                if cls._impl is None:
+                    import torch
+                    import torch.distributed as dist
+                    want_fused = os.environ.get("JENGA_ULYSSES", "fused") != "nccl"
+                    ok = 0
+                    if want_fused and dist.is_initialized() and dist.get_backend() == "nccl":
+                        try:
+                            import torch.distributed._symmetric_memory as symm
+                            symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+                            ok = 1
+                        except Exception:  # noqa: BLE001
+                            ok = 0
+                        t = torch.tensor([ok], device="cuda")
+                        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                        ok = int(t.item())
+                    cls._impl = U.UlyssesFusedAttention() if ok else U.UlyssesCarvedAttention(group=None)
+                return cls._impl
+
+            def forward(self, attn, query, key, value, **kw):
+                return self._get()(attn, query, key, value, **kw)
+
+            __call__ = forward
         modname = "hyvideo.modules.xdit_ring_atten"
         sys.modules[modname] = _module(modname, xFuserLongContextAttention=xFuserLongContextAttention)
         done.append(modname)
@@ -79,6 +114,14 @@ def install(flash_attn: bool = True, gilbert: bool = True, ulysses: bool = True)
     if gilbert:
         sys.modules["gilbert"] = G
         done.append("gilbert")
+    if fused_blocks:
+        from . import blocks
+        blocks.install_block_hook()
+        done.append("block-forward hook")
+    if gather:
+        from . import blocks
+        blocks.install_gather_hook()
+        done.append("gather hook")
     return done
 
 

@@ -157,6 +157,10 @@ def reference_packages(product: bool = False):
     install_environment_stubs()
     saved = _purge_packages()
     saved_extra = {k: sys.modules.get(k) for k in ("flash_attn", "flash_attn.flash_attn_interface", "gilbert")}
+    # a pure-reference import must not be touched by the product's block-forward hook
+    parked = [f for f in sys.meta_path if type(f).__name__ == "_PatchFinder"] if not product else []
+    for f in parked:
+        sys.meta_path.remove(f)
     try:
         if product:
             from jenga_b200 import install as _inst
@@ -172,6 +176,8 @@ def reference_packages(product: bool = False):
                 sys.modules[name] = m
         yield root
     finally:
+        for f in parked:
+            sys.meta_path.insert(0, f)
         _purge_packages()
         sys.modules.update(saved)
         for k, v in saved_extra.items():
