@@ -289,6 +289,43 @@ typedef struct JengaWanPrologueArgs {
 
 int jenga_wan_prologue(const JengaWanPrologueArgs* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (a-13) step-skip residual cache and TeaCache gate as device ops.
+ * ref: jenga_hyvideo.py:128-179 (`img += self.previous_residual`; `self.previous_residual =
+ *      img - ori_img`), jenga_hyvideo_multigpu.py:225-280, jenga_wan.py:595-648.
+ * residual_apply:  x[i] += residual[i]          (in place; fp32 add, one rounding to `dtype`)
+ * residual_store:  residual[i] = x_new[i] - x_old[i]
+ * n = element count; dtype bf16/f16 (16-byte aligned pointers) or f32.
+ * ---------------------------------------------------------------------------------------- */
+int jenga_residual_apply(void* x, const void* residual, int64_t n, int32_t dtype, void* stream);
+int jenga_residual_store(const void* x_new, const void* x_old, void* residual, int64_t n,
+                         int32_t dtype, void* stream);
+
+/* TeaCache gate of ONE parity (conditional / unconditional forward), jenga_wan.py:597-626:
+ *   if force:  calc = 1, accum = 0                (cnt < ret_steps, cnt >= cutoff_steps, stage start)
+ *   else:      rel = mean|cur-prev| / mean|prev|  (fp32 quotient, like the reference's .item())
+ *              accum += polyval(coeff, rel)       (coeff[0] = highest power, numpy.poly1d; float64)
+ *              calc = accum >= thresh ; if calc: accum = 0
+ *   prev <- cur when update_prev (the reference's `.clone()`).
+ * cur/prev: n elements of `dtype` (f32 or bf16).  state: double[1] on the device (accum).
+ * flag: int32, device or mapped pinned host memory (written before the kernel ends).
+ * rel_out: optional double[1] (diagnostics). */
+typedef struct JengaTeaCacheArgs {
+  const void* cur;
+  void* prev;
+  int32_t dtype;
+  int64_t n;
+  double coeff[8];
+  int32_t n_coeff;
+  double thresh;
+  int32_t force;
+  int32_t update_prev;
+  double* state;
+  int32_t* flag;
+  double* rel_out;
+} JengaTeaCacheArgs;
+int jenga_teacache_gate(const JengaTeaCacheArgs* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

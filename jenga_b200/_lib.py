@@ -92,6 +92,15 @@ class JengaWanPrologueArgs(C.Structure):
     ]
 
 
+class JengaTeaCacheArgs(C.Structure):
+    _fields_ = [
+        ("cur", C.c_void_p), ("prev", C.c_void_p), ("dtype", C.c_int32), ("n", C.c_int64),
+        ("coeff", C.c_double * 8), ("n_coeff", C.c_int32), ("thresh", C.c_double),
+        ("force", C.c_int32), ("update_prev", C.c_int32),
+        ("state", C.c_void_p), ("flag", C.c_void_p), ("rel_out", C.c_void_p),
+    ]
+
+
 def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise JengaError(
@@ -137,6 +146,12 @@ def _load() -> C.CDLL:
     lib.jenga_gilbert_block_neighbors_csr_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.jenga_gilbert_block_neighbors_csr_host.restype = C.c_int
+    lib.jenga_residual_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.jenga_residual_apply.restype = C.c_int
+    lib.jenga_residual_store.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.jenga_residual_store.restype = C.c_int
+    lib.jenga_teacache_gate.argtypes = [C.POINTER(JengaTeaCacheArgs), C.c_void_p]
+    lib.jenga_teacache_gate.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 1:
