@@ -210,46 +210,77 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU legs (oracle port / reference SDPA path) — bounded samples
+# CPU legs — bounded samples of the SAME workload on the host cores.
+#   kind "sdpa-port": the reference's CPU-runnable path for this operator, torch SDPA with the
+#                     expanded block mask (hyvideo/modules/attenion.py:102-107,
+#                     wan/modules/attention.py:167-176), on the workload's REAL selection mask
+#                     (oracle builder on the same synthetic tokens) for a sample of query blocks.
+#   kind "port":      the oracle's tile loop (oracle/attention_oracle.carved_attention_rows).
+# Both use every host core (torch.set_num_threads(os.cpu_count())) and report it.
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(wl, kind: str, budget_s: float = 12.0):
-    """Times a bounded sample of the SAME operator math on the host cores: one head, a few query
-    blocks at the workload's key length and density.  kind="port": oracle tile loop;
-    kind="sdpa": torch SDPA with the expanded block mask (the reference's CPU-runnable path)."""
+_CPU_CASE = {}
+
+
+def _cpu_case(wl, nq):
+    """One head of the workload on the CPU: tokens, the oracle-built mask rows of `nq` evenly spaced
+    query blocks, and their live-tile count."""
+    key = (wl["name"], wl["drop"], nq)
+    if key in _CPU_CASE:
+        return _CPU_CASE[key]
     from oracle import attention_oracle as orc
-    ncores = os.cpu_count() or 1
-    # the tile loop of the port is many small GEMMs: past ~32 threads it only adds sync cost
-    torch.set_num_threads(ncores if kind == "sdpa" else min(32, ncores))
+    from jenga_b200 import gilbert
     t, h, w = wl["grid"]
     n_img = t * h * w
     S = n_img + wl["text_tokens"]
     nb = (S + BLOCK - 1) // BLOCK
-    nb_img = (n_img + BLOCK - 1) // BLOCK
-    nq = 4 if kind == "sdpa" else 1
-    g = torch.Generator().manual_seed(5)
-    q = torch.randn(1, 1, nq * BLOCK, 128, generator=g).bfloat16()
-    k = torch.randn(1, 1, nb * BLOCK, 128, generator=g).bfloat16()
-    v = torch.randn(1, 1, nb * BLOCK, 128, generator=g).bfloat16()
-    live = max(1, int(round((1 - wl["drop"]) * nb_img))) + wl["text_blocks"]
-    mask = torch.zeros(1, 1, nq, nb, dtype=torch.bool)
-    for i in range(nq):
-        idx = torch.randperm(nb_img, generator=g)[: live - wl["text_blocks"]]
-        mask[0, 0, i, idx] = True
-        mask[0, 0, i, nb_img:] = True
-    flops = 4 * BLOCK * BLOCK * 128 * int(mask.sum())
+    tb = wl["text_blocks"]
+    n_img_b = nb - tb
+    cpu = torch.device("cpu")
+    q = synth_tokens(nb * BLOCK, 1, cpu, 1234)[:, :, 0].unsqueeze(1)   # [1,1,Sp,128] bf16
+    k = synth_tokens(nb * BLOCK, 1, cpu, 1235)[:, :, 0].unsqueeze(1)
+    v = torch.randn(1, 1, nb * BLOCK, 128, generator=torch.Generator().manual_seed(1236)).bfloat16()
+    if S < nb * BLOCK:
+        for x in (q, k, v):
+            x[:, :, S:] = 0
+    nbr = gilbert.block_neighbor_mapping(t, h, w, sliced=bool(wl["sliced"]))
+    if wl["variant"] == "wan":
+        top_k = math.ceil(int(n_img_b * (1 - wl["drop"])))
+    else:
+        top_k = int((1 - wl["drop"]) * (n_img // BLOCK))
+    mask = orc.build_block_onehot(q[:, :, :n_img_b * BLOCK], k, top_k, n_img_b, nb, wl["p_remain"], tb, nbr,
+                                  wl["first_frame"])                       # [1,1,n_img_b,nb]
+    rows = sorted({int(round(i * (n_img_b - 1) / max(nq - 1, 1))) for i in range(nq)})
+    qs = torch.cat([q[:, :, r * BLOCK:(r + 1) * BLOCK] for r in rows], dim=2)
+    ms = mask[:, :, rows]
+    seqlen = n_img + wl["text_valid"] if wl["variant"] != "wan" else S
+    _CPU_CASE[key] = dict(q=qs, k=k, v=v, mask=ms, rows=rows, live=int(ms.sum()), S=S, nb=nb, n_img_b=n_img_b,
+                          seqlen=seqlen)
+    return _CPU_CASE[key]
+
+
+def cpu_sample(wl, kind: str, nq: int, min_seconds: float):
+    """Returns (TFLOP/s algorithmic, sample description, seconds per rep, threads)."""
+    from oracle import attention_oracle as orc
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    c = _cpu_case(wl, nq)
+    flops = 4 * BLOCK * BLOCK * 128 * c["live"]
     reps, t_total = 0, 0.0
-    while reps == 0 or (t_total < budget_s and reps < 50):
+    while reps == 0 or t_total < min_seconds:
         t0 = time.perf_counter()
         if kind == "port":
-            orc.carved_attention_rows(q, k, v, mask, S, 128 ** -0.5, 0.0, nb_img)
+            orc.carved_attention_rows(c["q"], c["k"], c["v"], c["mask"], c["seqlen"], 128 ** -0.5, wl["text_amp"],
+                                      c["n_img_b"])
         else:
-            big = mask.repeat_interleave(BLOCK, 2).repeat_interleave(BLOCK, 3)
-            torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=big)
+            big = c["mask"].repeat_interleave(BLOCK, 2).repeat_interleave(BLOCK, 3)
+            big[..., c["seqlen"]:] = False
+            torch.nn.functional.scaled_dot_product_attention(c["q"], c["k"], c["v"], attn_mask=big)
         t_total += time.perf_counter() - t0
         reps += 1
     tf = flops * reps / t_total / 1e12
-    sample = (f"1 head x {nq} query blocks x {live} live key blocks of {nb} (S={S}), "
-              f"{reps} reps, {t_total:.1f}s")
+    sample = (f"1 head x {len(c['rows'])} query blocks (evenly spaced) x their {c['live']} live key tiles of the "
+              f"workload's own mask (nb={c['nb']}, S={c['S']}), {reps} reps, {t_total:.1f}s, "
+              f"{torch.get_num_threads()} threads")
     return tf, sample, t_total / reps, torch.get_num_threads()
 
 
@@ -331,6 +362,119 @@ def gpu_reference_leg(wl, inp, iters=3):
 
 
 # ------------------------------------------------------------------------------------------------
+# DiT block-stack leg: the UNMODIFIED reference block classes (MMDoubleStreamBlock /
+# MMSingleStreamBlock, random-init at the HunyuanVideo width) run (A) with the reference's own
+# operator (Triton + FA2) and (B) through jenga_b200.install (operator + fused prologue + gather
+# hooks), same weights, same inputs, same GPU.  This is the measured DiT-loop number: one computed
+# denoising step = 20 double + 40 single blocks (jenga_hyvideo.py:132-178); a video = 23 of them.
+# ------------------------------------------------------------------------------------------------
+def dit_forward_leg(wl, inp, n_double, n_single, hidden=3072, heads=24):
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return {"unavailable": "oracle/_ref/ not staged"}
+        ref_hy, _ = ref_loader.load_blocks(product=False)
+        our_hy, _ = ref_loader.load_blocks(product=True)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    from jenga_b200 import blocks as jb
+    from jenga_b200 import gilbert
+    dev = inp["q"].device
+    t, h, w = wl["grid"]
+    L, T = inp["n_img"], wl["text_tokens"]
+    g = torch.Generator(device=dev).manual_seed(2024)
+
+    def init(m):
+        with torch.no_grad():
+            for n_, p_ in m.named_parameters():
+                if p_.dim() >= 2:
+                    p_.copy_(torch.randn(p_.shape, generator=g, device=dev, dtype=torch.float32).mul_(0.02))
+                elif "norm" in n_:
+                    p_.fill_(1.0)
+                else:
+                    p_.zero_()
+
+    def stack(mod):
+        d = [mod.MMDoubleStreamBlock(hidden, heads, mlp_width_ratio=4.0, dtype=torch.bfloat16, device=dev)
+             for _ in range(n_double)]
+        s_ = [mod.MMSingleStreamBlock(hidden, heads, mlp_width_ratio=4.0, dtype=torch.bfloat16, device=dev)
+              for _ in range(n_single)]
+        return d, s_
+
+    try:
+        rd, rs = stack(ref_hy)
+        for b_ in rd + rs:
+            init(b_)
+        with torch.device("meta"):
+            od = [our_hy.MMDoubleStreamBlock(hidden, heads, mlp_width_ratio=4.0, dtype=torch.bfloat16) for _ in range(n_double)]
+            os_ = [our_hy.MMSingleStreamBlock(hidden, heads, mlp_width_ratio=4.0, dtype=torch.bfloat16) for _ in range(n_single)]
+        for a_, b_ in zip(od + os_, rd + rs):
+            a_.load_state_dict(b_.state_dict(), assign=True)     # shared weights, no second copy
+        l2h, h2l = gilbert.mapping_tensors(t, h, w)
+        l2h, h2l = l2h.to(dev), h2l.to(dev)
+        curve_sel = [[l2h, h2l, inp["nbr"]]]
+        img0 = torch.randn(1, L, hidden, generator=g, device=dev).bfloat16()
+        txt0 = torch.randn(1, T, hidden, generator=g, device=dev).bfloat16()
+        vec = torch.randn(1, hidden, generator=g, device=dev).bfloat16()
+        ang = torch.rand(L, 64, generator=g, device=dev) * 6.2831853
+        cos = torch.cos(ang).repeat_interleave(2, dim=1).contiguous()
+        sin = torch.sin(ang).repeat_interleave(2, dim=1).contiguous()
+        cu = inp["cu"]
+        drop = wl["drop"]
+
+        def forward(dbl, sgl, hooks):
+            """the block loop of ra_forward (jenga_hyvideo.py:116-118,132-178,226)"""
+            if hooks:
+                jb.install_gather_hook()
+            else:
+                jb.remove_gather_hook()
+            img = img0[:, h2l]
+            fc, fs = cos[h2l], sin[h2l]
+            txt = txt0
+            for blk in dbl:
+                img, txt = blk(img, txt, vec, cu, cu, L + T, L + T, (fc, fs), drop, wl["text_amp"], curve_sel, wl["p_remain"])
+            x = torch.cat((img, txt), 1)
+            for blk in sgl:
+                x = blk(x, vec, T, cu, cu, L + T, L + T, (fc, fs), drop, wl["text_amp"], curve_sel, wl["p_remain"])
+            return x[:, :L][:, l2h]
+
+        def timed(fn, n):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / n, r
+
+        nblk = n_double + n_single
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            forward(rd[:1], rs[:1], False)                                    # Triton JIT + cuBLAS warm-up
+            ref_s, ref_out = timed(lambda: forward(rd, rs, False), 1)
+            forward(od, os_, True)
+            our_s, our_out = timed(lambda: forward(od, os_, True), 2)
+        jb.remove_gather_hook()
+        rms = ref_out.float().pow(2).mean().sqrt().item()
+        diff = (our_out.float() - ref_out.float()).abs()
+        scale = (20 + 40) / nblk
+        return {"blocks_measured": {"double": n_double, "single": n_single}, "hidden": hidden, "heads": heads,
+                "reference_seconds": ref_s, "ours_seconds": our_s, "speedup": ref_s / our_s,
+                "seconds_per_computed_step": {"reference": ref_s * scale, "ours": our_s * scale,
+                                              "note": "measured blocks x (60 / measured), blocks are homogeneous"},
+                "dit_loop_sec_per_video": {"reference": ref_s * scale * wl["computed_steps"],
+                                           "ours": our_s * scale * wl["computed_steps"],
+                                           "computed_steps": wl["computed_steps"]},
+                "output_vs_reference": {"max_over_rms": diff.max().item() / rms, "mean_over_rms": diff.mean().item() / rms},
+                "fused_calls": {k_: v_ for k_, v_ in jb.STATS.items()},
+                "what": "unmodified reference block classes, random-init bf16 weights; A = reference operator "
+                        "(Triton+FA2), B = the same classes through jenga_b200.install hooks"}
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}", "trace": traceback.format_exc()[-600:]}
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,6 +489,9 @@ def main():
                          "(23 = the whole 50-step video: 1380 hot-path calls) and report measured "
                          "hot-path seconds per video")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dit-blocks", default="4,8",
+                    help="DiT block-stack leg: 'D,S' double,single blocks to build and time for both the "
+                         "reference and this library (default 4,8 = 1/5 of a forward; 'full' = 20,40; 'none')")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip timing the unmodified reference operator (Triton + FA2) on this GPU")
     args = ap.parse_args()
@@ -358,12 +505,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        nq = int(os.environ.get("JENGA_REF_NQ", "32"))
+        for _ in range(max(1, min(args.warmup, 2))):
+            cpu_sample(wl, "sdpa-port", nq, 0.0)
         vals = []
-        ncores = os.cpu_count()
-        for _ in range(max(1, args.warmup)):
-            cpu_sample(wl, "sdpa", budget_s=0.0)
         for _ in range(max(1, args.steps)):
-            tf_i, sample, sec, ncores = cpu_sample(wl, "sdpa", budget_s=0.0)
+            tf_i, sample, sec, ncores = cpu_sample(wl, "sdpa-port", nq, 3.0)   # one step >= 3 s of CPU work
             vals.append((tf_i, sec))
         tf = sum(v[0] for v in vals) / len(vals)
         ms = 1e3 * sum(v[1] for v in vals) / len(vals)
@@ -372,9 +519,9 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": wl["name"], "sa_drop": wl["drop"], "p_remain": wl["p_remain"],
                            "text_blocks": wl["text_blocks"], "parallelism": "host cpu",
-                           "sample": "bounded: 1 head x 4 query blocks at the workload's key length and density"},
-                "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
-                                 "sample": "torch SDPA + expanded block mask (reference CPU path, "
+                           "sample": f"bounded: 1 head x {nq} query blocks of the workload's own mask, >= 3 s per step"},
+                "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "sdpa-port",
+                                 "sample": "torch SDPA + expanded block mask (the reference's CPU-runnable path, "
                                            "hyvideo/modules/attenion.py:102-107): " + sample},
                 "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -568,9 +715,19 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        tf, sample, _, ncores = cpu_sample(wl, "port")
-        cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
-               "sample": "oracle/attention_oracle.carved_attention_rows: " + sample}
+        tf, sample, _, ncores = cpu_sample(wl, "sdpa-port", 16, 6.0)
+        cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "sdpa-port",
+               "sample": "torch SDPA + expanded block mask (same function as --impl reference): " + sample}
+        tf_p, sample_p, _, _ = cpu_sample(wl, "port", 2, 4.0)
+        cpu["oracle_port"] = {"value": tf_p, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
+                              "sample": "oracle/attention_oracle.carved_attention_rows: " + sample_p}
+
+    ditf = None
+    if rank == 0 and world == 1 and args.dit_blocks != "none" and wl["variant"] == "hyvideo" and not args.no_gpu_reference:
+        nd, ns = (20, 40) if args.dit_blocks == "full" else (int(v_) for v_ in args.dit_blocks.split(","))
+        torch.cuda.empty_cache()
+        ditf = dit_forward_leg(wl, inp, nd, ns)
+        torch.cuda.empty_cache()
 
     gref = None
     if rank == 0 and world == 1 and not args.no_gpu_reference:
@@ -601,6 +758,8 @@ def main():
             line["cpu_baseline"] = cpu
         if dit:
             line["dit_loop"] = dit
+        if ditf:
+            line["dit_forward"] = ditf
         if gref:
             line["gpu_reference"] = gref
             line["vs_gpu_reference"] = gref.get("speedup_of_this_operator")

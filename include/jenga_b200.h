@@ -307,7 +307,8 @@ int jenga_residual_store(const void* x_new, const void* x_old, void* residual, i
  *              accum += polyval(coeff, rel)       (coeff[0] = highest power, numpy.poly1d; float64)
  *              calc = accum >= thresh ; if calc: accum = 0
  *   prev <- cur when update_prev (the reference's `.clone()`).
- * cur/prev: n elements of `dtype` (f32 or bf16).  state: double[1] on the device (accum).
+ * cur/prev: n elements, dtype must be JENGA_F32 (the reference asserts fp32 embeddings).
+ * state: double[1] on the device (accum).
  * flag: int32, device or mapped pinned host memory (written before the kernel ends).
  * rel_out: optional double[1] (diagnostics). */
 typedef struct JengaTeaCacheArgs {

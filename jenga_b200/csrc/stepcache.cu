@@ -105,7 +105,6 @@ int launch_residual(const void* a, const void* b, void* out, long long n, int dt
 template <typename T>
 __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 template <typename T>
 __global__ void __launch_bounds__(1024)
@@ -175,14 +174,12 @@ extern "C" int jenga_teacache_gate(const JengaTeaCacheArgs* a, void* stream) {
   if (a->n <= 0 || a->n_coeff < 1 || a->n_coeff > 8)
     return set_error(JENGA_E_INVALID, "teacache_gate: bad sizes");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->dtype == JENGA_F32)
-    teacache_gate_kernel<float><<<1, 1024, 0, s>>>(static_cast<const float*>(a->cur),
-                                                   static_cast<float*>(a->prev), a->n, *a);
-  else if (a->dtype == JENGA_BF16)
-    teacache_gate_kernel<__nv_bfloat16><<<1, 1024, 0, s>>>(static_cast<const __nv_bfloat16*>(a->cur),
-                                                           static_cast<__nv_bfloat16*>(a->prev), a->n, *a);
-  else
-    return set_error(JENGA_E_INVALID, "teacache_gate: dtype must be f32 or bf16");
+  // the reference asserts fp32 embeddings (wan/modules/model_mul.py: `assert e.dtype == torch.float32
+  // and e0.dtype == torch.float32`); 16-bit inputs would take ATen's 16-bit mean/divide roundings,
+  // which this kernel does not restate
+  if (a->dtype != JENGA_F32) return set_error(JENGA_E_UNSUPPORTED, "teacache_gate: embeddings must be f32");
+  teacache_gate_kernel<float><<<1, 1024, 0, s>>>(static_cast<const float*>(a->cur), static_cast<float*>(a->prev),
+                                                 a->n, *a);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "teacache_gate launch");
 }

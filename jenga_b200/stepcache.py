@@ -143,8 +143,8 @@ class TeaCache:
         """should_calc for the current forward; also performs `previous_e0 = modulated_inp.clone()`."""
         _require_cuda(modulated_inp)
         x = modulated_inp.contiguous()
-        if x.dtype not in (torch.float32, torch.bfloat16):
-            raise ValueError("modulated input must be fp32 or bf16")
+        if x.dtype != torch.float32:
+            raise ValueError("modulated input must be fp32 (the reference asserts e/e0 are fp32)")
         par = self.cnt % 2
         force = self.cnt < self.ret_steps or self.cnt >= self.cutoff_steps or self.stage_start or self._prev[par] is None
         if self._prev[par] is None or self._prev[par].shape != x.shape or self._prev[par].dtype != x.dtype:

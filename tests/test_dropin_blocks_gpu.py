@@ -10,8 +10,9 @@ twice from the reference tree (oracle/ref_loader.py) —
 
 given the SAME random-init weights and inputs on the GPU, and compared.  Tolerance: rows whose
 selection masks are identical in every head (>= 90 % of rows; the rest differ only by the
-reference's unstable tie order) obey |B - A| <= 3e-2*RMS max, 3e-3*RMS mean on the block OUTPUT
-(attention error 2e-2/2e-3 propagated through proj + MLP + residual)."""
+reference's unstable tie order) obey |B - A| <= 3e-2*RMS + 2^-7*|A| per element and 3e-3*RMS mean on
+the block OUTPUT (the attention tolerance of test_reference_gpu.py propagated through proj + MLP +
+residual, plus one bf16 ulp of the output)."""
 import sys
 from pathlib import Path
 
@@ -85,16 +86,20 @@ def _rows_with_equal_masks(ref_mask, our_bits, nb):
 
 
 def _compare(a, b, row_ok, what):
+    """per element |B - A| <= 3e-2*RMS + 2^-7*|A| (the |A| term admits one bf16 ulp flip of the
+    block output, which carries the residual stream), mean <= 3e-3*RMS, on rows with equal masks"""
     a, b = a.float(), b.float()
     rms = a.pow(2).mean().sqrt().item()
     d = (a - b).abs()[0]                              # [rows, C]
     sel = row_ok[:, None]
     frac = row_ok.float().mean().item()
+    bad = ((d > 3e-2 * rms + 2.0 ** -7 * a.abs()[0]) & sel).sum().item()
     mx = (d * sel).max().item() / rms
     mean = ((d * sel).sum() / (sel.sum() * d.shape[1]).clamp_min(1)).item() / rms
-    print(f"\n[drop-in] {what}: rows with identical masks {frac:.3f}, max {mx:.3e} mean {mean:.3e} (x RMS)")
+    print(f"\n[drop-in] {what}: rows with identical masks {frac:.3f}, max {mx:.3e} mean {mean:.3e} (x RMS), "
+          f"{bad} elements over the bound")
     assert frac >= 0.90, (what, frac)
-    assert mx <= 3e-2 and mean <= 3e-3, (what, mx, mean)
+    assert bad == 0 and mean <= 3e-3, (what, mx, mean, bad)
 
 
 def _hy_case(hy_mod):

@@ -50,8 +50,7 @@ def _reference_gate(seq, coeffs, thresh, ret_steps, cutoff_steps):
     return out, accs
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_teacache_gate_matches_reference_state_machine(dtype):
+def test_teacache_gate_matches_reference_state_machine(dtype=torch.float32):
     from jenga_b200.stepcache import TeaCache
     coeffs = [-5.21862437e+04, 9.23041404e+03, -5.28275948e+02, 1.36987616e+01, -4.99875664e-02]  # jenga_wan.py:1087
     steps, ret, cut, thresh = 30, 10, 60, 0.15
