@@ -658,18 +658,40 @@ def main():
         # every rank stages ITS token slice (all heads) + the replicated text rows from pinned host
         # memory, runs the sequence-parallel operator and returns its slice of the result to the host
         hq, hk, hv = (state[n].cpu().pin_memory() for n in ("q", "k", "v"))
-        dq, dk, dv = (torch.empty_like(state[n]) for n in ("q", "k", "v"))
-        hout = torch.empty((1, state["q"].shape[1], inp["heads"] * 128), dtype=torch.bfloat16).pin_memory()
-        def e2e_step():
-            dq.copy_(hq, non_blocking=True)
-            dk.copy_(hk, non_blocking=True)
-            dv.copy_(hv, non_blocking=True)
-            st2 = dict(state, q=dq, k=dk, v=dv)
-            hout.copy_(ulysses.bench_step(wl, st2), non_blocking=True)
+        n_rows = state["q"].shape[1]
+        hout = torch.empty((1, n_rows, inp["heads"], 128), dtype=torch.bfloat16).pin_memory()
+        e2e_api = None
+        if state["mode"].startswith("fused"):
+            # public API: ulysses.HostPipelinedUlysses — H2D / peer-store exchange / attention / D2H of
+            # consecutive head sub-groups on four streams, copy-in running ahead into the next step
+            pipe = ulysses.HostPipelinedUlysses(state["n_loc"], n_rows - state["n_loc"], inp["heads"], 128,
+                                                torch.bfloat16, dev, fused=state["sp"])
+            kw_ = dict(top_k=state["top_k"], text_amp=wl["text_amp"], block_neighbor_list=inp["nbr"],
+                       p_remain_rates=wl["p_remain"], cu_seqlens_q=state["cu"], cu_seqlens_kv=state["cu"])
+            def e2e_step():
+                pipe(hq, hk, hv, hout, **kw_)
+            e2e_api = f"ulysses.HostPipelinedUlysses ({pipe.G} head sub-groups per rank, 4 streams; max over ranks)"
+        else:
+            dq, dk, dv = (torch.empty_like(state[n]) for n in ("q", "k", "v"))
+            def e2e_step():
+                dq.copy_(hq, non_blocking=True)
+                dk.copy_(hk, non_blocking=True)
+                dv.copy_(hv, non_blocking=True)
+                st2 = dict(state, q=dq, k=dk, v=dv)
+                hout.view(1, n_rows, -1).copy_(ulysses.bench_step(wl, st2), non_blocking=True)
+            e2e_api = "ulysses.my_parallel_attention (NCCL) on per-rank pinned host slices (max over ranks)"
         for _ in range(2):
             e2e_step()
         barrier()
-        n_it = max(3, min(args.steps, 5))
+        e2e_ok = None
+        if state["mode"].startswith("fused"):
+            want = ulysses.bench_step(wl, state).view(1, n_rows, inp["heads"], 128)
+            torch.cuda.synchronize()
+            e2e_ok = bool(torch.equal(hout, want.cpu()))
+            tt = torch.tensor([1 if e2e_ok else 0], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            e2e_ok = bool(tt.item())
+        n_it = max(3, min(args.steps, 10))
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record()
         for _ in range(n_it):
@@ -683,7 +705,7 @@ def main():
         e2e = {"value": flops / (ems * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ems,
                "h2d_bytes_per_step": world * sum(x.numel() * x.element_size() for x in (hq, hk, hv)),
                "d2h_bytes_per_step": world * hout.numel() * hout.element_size(),
-               "api": "ulysses.my_parallel_attention on per-rank pinned host slices (max over ranks)"}
+               "api": e2e_api, "matches_device_resident_result": e2e_ok}
 
     dit = None
     if args.dit_loop > 0 and world == 1 and wl["variant"] == "hyvideo":
@@ -718,22 +740,6 @@ def main():
         tf, sample, _, ncores = cpu_sample(wl, "sdpa-port", 16, 6.0)
         cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "sdpa-port",
                "sample": "torch SDPA + expanded block mask (same function as --impl reference): " + sample}
-        tf_p, sample_p, _, _ = cpu_sample(wl, "port", 2, 4.0)
-        cpu["oracle_port"] = {"value": tf_p, "unit": "TFLOP/s", "cores": ncores, "kind": "port",
-                              "sample": "oracle/attention_oracle.carved_attention_rows: " + sample_p}
-
-    ditf = None
-    if rank == 0 and world == 1 and args.dit_blocks != "none" and wl["variant"] == "hyvideo" and not args.no_gpu_reference:
-        nd, ns = (20, 40) if args.dit_blocks == "full" else (int(v_) for v_ in args.dit_blocks.split(","))
-        torch.cuda.empty_cache()
-        ditf = dit_forward_leg(wl, inp, nd, ns)
-        torch.cuda.empty_cache()
-
-    gref = None
-    if rank == 0 and world == 1 and not args.no_gpu_reference:
-        gref = gpu_reference_leg(wl, inp)
-        if "total_ms" in gref:
-            gref["speedup_of_this_operator"] = gref["total_ms"] / ms
 
     if rank == 0:
         value = flops / (ms * 1e-3) / 1e12

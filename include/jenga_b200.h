@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define JENGA_B200_ABI_VERSION 1
+#define JENGA_B200_ABI_VERSION 2
 
 enum {
   JENGA_OK = 0,
@@ -132,6 +132,15 @@ typedef struct JengaAttnArgs {
   int32_t sp_world, sp_rank, sp_heads_total;
   int64_t sp_rows;
   const uint64_t* out_peers_host;
+  /* ABI 2: global head index of this launch's head 0 in the owners' buffers; -1 (or the struct
+   * zero-filled with sp_head_base_valid == 0) means sp_rank*heads.  Lets one rank's head group be
+   * processed as several launches (head sub-groups pipelined against the inbound exchange); then
+   * sp_heads_total is the true total and need not equal heads*sp_world. */
+  int32_t sp_head_base, sp_head_base_valid;
+  /* ABI 2, dense shims: optional fp32 [B, H, q_rows] log-sum-exp (natural log) of every DENSE
+   * row, what flash_attn's _flash_attn_forward returns as softmax_lse
+   * (ref hyvideo/modules/attenion.py:221-246).  NULL = not written. */
+  float* lse_out;
 } JengaAttnArgs;
 
 int jenga_carved_attn_fwd(const JengaAttnArgs* args, void* stream);
@@ -211,6 +220,9 @@ typedef struct JengaUlyssesScatterArgs {
   int32_t world, rank, heads, head_dim;
   int64_t n_loc, n_text;
   const uint64_t* peer_qkv_host;
+  /* head-group form (ABI 2): move only the local heads [head_begin, head_begin+head_count) of
+   * every destination rank's group; head_count == 0 moves all heads/world of them. */
+  int32_t head_begin, head_count;
 } JengaUlyssesScatterArgs;
 
 int jenga_ulysses_scatter(const JengaUlyssesScatterArgs* args, void* stream);

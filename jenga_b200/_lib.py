@@ -39,6 +39,8 @@ class JengaAttnArgs(C.Structure):
         ("err_flag", C.c_void_p),
         ("sp_world", C.c_int32), ("sp_rank", C.c_int32), ("sp_heads_total", C.c_int32),
         ("sp_rows", C.c_int64), ("out_peers_host", C.c_void_p),
+        ("sp_head_base", C.c_int32), ("sp_head_base_valid", C.c_int32),
+        ("lse_out", C.c_void_p),
     ]
 
 
@@ -48,6 +50,7 @@ class JengaUlyssesScatterArgs(C.Structure):
         ("x_stride_s", C.c_int64), ("joint_stride_s", C.c_int64),
         ("world", C.c_int32), ("rank", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
         ("n_loc", C.c_int64), ("n_text", C.c_int64), ("peer_qkv_host", C.c_void_p),
+        ("head_begin", C.c_int32), ("head_count", C.c_int32),
     ]
 
 
@@ -154,7 +157,7 @@ def _load() -> C.CDLL:
     lib.jenga_teacache_gate.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
-    if lib.jenga_abi_version() != 1:
+    if lib.jenga_abi_version() != 2:
         raise JengaError("libjenga_b200.so ABI version mismatch")
     return lib
 

@@ -306,7 +306,7 @@ def block_sparse_attention_variant(
 
 
 def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_block_start,
-            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype, sp_out=None):
+            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype, sp_out=None, lse_out=None):
     B, Sq, H, D = q.shape
     a = JengaAttnArgs()
     a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
@@ -324,6 +324,9 @@ def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_bl
         a.sp_world, a.sp_rank = sp_out["world"], sp_out["rank"]
         a.sp_heads_total, a.sp_rows = sp_out["heads_total"], sp_out["rows"]
         a.out_peers_host = C.addressof(sp_out["peers"])
+        if "head_base" in sp_out:
+            a.sp_head_base, a.sp_head_base_valid = int(sp_out["head_base"]), 1
+    a.lse_out = lse_out.data_ptr() if lse_out is not None else None
     a.nq_sparse, a.nq_dense = nq_sparse, nq_dense
     a.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
     a.mask_words = mask_bits.shape[-1] if mask_bits is not None else 0

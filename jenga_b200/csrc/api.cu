@@ -94,43 +94,52 @@ onehot_to_bits_kernel(const uint8_t* __restrict__ onehot, uint32_t* __restrict__
 }
 
 // Ulysses inbound exchange: one pass over the local q,k,v, 16-byte stores into peer memory.
+// A call moves the local heads [hg0, hg0+hg) of EVERY destination rank's head group (hg == h_loc
+// moves everything); the head-group form lets the exchange of group g+1 run on a second stream
+// under the attention of group g.
 struct ScatterParams {
   const uint4* x[3];
   const uint4* joint[3];
   long long x_stride_v, joint_stride_v;  // uint4 units between tokens
   int world, rank, heads, vec_per_head;  // vec_per_head = head_dim*2/16
+  int hg0, hg;                           // local head range of this call
   long long n_loc, n_text;
   unsigned long long peer[8];
 };
 __global__ void __launch_bounds__(256)
 ulysses_scatter_kernel(const ScatterParams p) {
   const int w = blockIdx.y;  // 0:q 1:k 2:v
-  const int vec_per_row = p.heads * p.vec_per_head;
   const int h_loc = p.heads / p.world;
+  const int vec_per_tok = p.world * p.hg * p.vec_per_head;     // vectors this call moves per image token
   const long long n_total = static_cast<long long>(p.world) * p.n_loc + p.n_text;
-  const long long img_vecs = p.n_loc * vec_per_row;
-  const long long txt_vecs = p.n_text * (static_cast<long long>(h_loc) * p.vec_per_head);
+  const long long img_vecs = p.n_loc * vec_per_tok;
+  const int txt_per_tok = p.hg * p.vec_per_head;
+  const long long txt_vecs = p.n_text * static_cast<long long>(txt_per_tok);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < img_vecs + txt_vecs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     if (i < img_vecs) {
-      const long long tok = i / vec_per_row;
-      const int c = static_cast<int>(i - tok * vec_per_row);
-      const int head = c / p.vec_per_head;
-      const int dst_rank = head / h_loc;
-      const int hl = head - dst_rank * h_loc;
-      const uint4 v = __ldg(p.x[w] + tok * p.x_stride_v + c);
+      const long long tok = i / vec_per_tok;
+      const int c = static_cast<int>(i - tok * vec_per_tok);
+      const int dst_rank = c / txt_per_tok;
+      const int r = c - dst_rank * txt_per_tok;
+      const int hl = p.hg0 + r / p.vec_per_head;               // local head at the destination
+      const int v_in_head = r - (r / p.vec_per_head) * p.vec_per_head;
+      const int head = dst_rank * h_loc + hl;                    // global head = column of x
+      const uint4 v = __ldg(p.x[w] + tok * p.x_stride_v + head * p.vec_per_head + v_in_head);
       uint4* dst = reinterpret_cast<uint4*>(p.peer[dst_rank]) +
                    ((static_cast<long long>(w) * n_total + p.rank * p.n_loc + tok) * h_loc + hl) * p.vec_per_head +
-                   (c - head * p.vec_per_head);
+                   v_in_head;
       *dst = v;
     } else {
       const long long k = i - img_vecs;
-      const int per_tok = h_loc * p.vec_per_head;
-      const long long tok = k / per_tok;
-      const int c = static_cast<int>(k - tok * per_tok);
-      const uint4 v = __ldg(p.joint[w] + tok * p.joint_stride_v + p.rank * per_tok + c);
+      const long long tok = k / txt_per_tok;
+      const int r = static_cast<int>(k - tok * txt_per_tok);
+      const int hl = p.hg0 + r / p.vec_per_head;
+      const int v_in_head = r - (r / p.vec_per_head) * p.vec_per_head;
+      const uint4 v = __ldg(p.joint[w] + tok * p.joint_stride_v + (p.rank * h_loc + hl) * p.vec_per_head + v_in_head);
       uint4* dst = reinterpret_cast<uint4*>(p.peer[p.rank]) +
-                   (static_cast<long long>(w) * n_total + p.world * p.n_loc + tok) * per_tok + c;
+                   ((static_cast<long long>(w) * n_total + p.world * p.n_loc + tok) * h_loc + hl) * p.vec_per_head +
+                   v_in_head;
       *dst = v;
     }
   }
@@ -231,9 +240,13 @@ extern "C" int jenga_ulysses_scatter(const JengaUlyssesScatterArgs* a, void* str
   p.x_stride_v = a->x_stride_s / 8;
   p.joint_stride_v = a->joint_stride_s / 8;
   p.world = a->world; p.rank = a->rank; p.heads = a->heads; p.vec_per_head = a->head_dim / 8;
+  const int h_loc = a->heads / a->world;
+  p.hg0 = a->head_count > 0 ? a->head_begin : 0;
+  p.hg = a->head_count > 0 ? a->head_count : h_loc;
+  if (p.hg0 < 0 || p.hg0 + p.hg > h_loc) return set_error(JENGA_E_INVALID, "ulysses_scatter: head group out of range");
   p.n_loc = a->n_loc; p.n_text = a->n_text;
   for (int r = 0; r < a->world; ++r) p.peer[r] = a->peer_qkv_host[r];
-  const long long total = a->n_loc * a->heads * p.vec_per_head + a->n_text * (a->heads / a->world) * p.vec_per_head;
+  const long long total = (a->n_loc * a->world + a->n_text) * p.hg * p.vec_per_head;
   long long blocks = (total + 255) / 256;
   if (blocks > 148ll * 16) blocks = 148ll * 16;
   dim3 grid(static_cast<unsigned>(blocks), 3);

@@ -442,6 +442,11 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     const bool in_tensor = q_row < p.q_rows;
     const bool zero_row = (n_tiles == 0) || (!dense && q_row >= q_limit_sparse);
     const float inv_l = zero_row ? 0.f : 1.0f / l_sum;
+    if (p.lse_out && dense && in_tensor) {
+      // softmax_lse of flash_attn (natural log): ln sum_j exp(s_j * sm_scale) = (m + log2 l) * ln 2
+      p.lse_out[(static_cast<long long>(b) * p.heads + h) * p.q_rows + q_row] =
+          zero_row ? -INFINITY : (m_used + log2f(l_sum)) * 0.6931471805599453f;
+    }
     // destination(s) of this row
     long long o_off = b * p.o_stride_b + q_row * p.o_stride_s + static_cast<long long>(h) * p.o_stride_h;
     uint16_t* obase = reinterpret_cast<uint16_t*>(p.out);
@@ -450,7 +455,7 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
       // Fused Ulysses exchange (ref xdit_ring_atten.py:206-219 does this with two all-to-alls
       // after the kernel): image row t belongs to rank t / sp_rows; text rows go to every rank.
       const long long n_img = p.sp_rows * p.sp_world;
-      const int gh = p.sp_rank * p.heads + h;
+      const int gh = p.sp_head_base + h;
       if (q_row < n_img) {
         const int owner = static_cast<int>(q_row / p.sp_rows);
         obase = reinterpret_cast<uint16_t*>(p.peer_out[owner]);
@@ -566,8 +571,13 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   if (!(a->sm_scale > 0.f)) return set_error(JENGA_E_INVALID, "sm_scale must be positive");
   if (a->sp_world != 0 &&
       (a->sp_world < 0 || a->sp_world > 8 || a->sp_rank < 0 || a->sp_rank >= a->sp_world || !a->out_peers_host ||
-       a->sp_rows <= 0 || a->sp_heads_total != a->heads * a->sp_world || a->batch != 1 || a->out_dtype != a->dtype))
+       a->sp_rows <= 0 || a->batch != 1 || a->out_dtype != a->dtype))
     return set_error(JENGA_E_INVALID, "bad Ulysses epilogue arguments");
+  const int sp_head_base = a->sp_head_base_valid ? a->sp_head_base : a->sp_rank * a->heads;
+  if (a->sp_world != 0 &&
+      ((!a->sp_head_base_valid && a->sp_heads_total != a->heads * a->sp_world) || sp_head_base < 0 ||
+       sp_head_base + a->heads > a->sp_heads_total))
+    return set_error(JENGA_E_INVALID, "bad Ulysses head range");
 
   // Kernel generation: 2 (default) or the experimental generation 6 via JENGA_ATTN_KERNEL=v6
   // (tuning switch, same results up to fp32 rounding; profiles/README.md has the comparison).
@@ -606,6 +616,7 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
     p.sp_world = a->sp_world;
     p.sp_rank = a->sp_rank;
     p.sp_heads_total = a->sp_heads_total;
+    p.sp_head_base = sp_head_base;
     p.sp_rows = a->sp_rows;
     for (int r = 0; r < a->sp_world; ++r) p.peer_out[r] = a->out_peers_host[r];
   }
@@ -616,6 +627,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   p.o_stride_s = a->o_stride_s;
   p.o_stride_h = a->o_stride_h;
   p.err_flag = a->err_flag;
+  p.lse_out = a->lse_out;
+  if (a->lse_out && gen != 2) return set_error(JENGA_E_UNSUPPORTED, "lse_out: default kernel generation only");
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
   if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");

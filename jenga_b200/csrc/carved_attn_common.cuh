@@ -27,8 +27,10 @@ struct KernelParams {
   // buffer over NVLink instead of `out`.  peer_out[r] = base of rank r's [sp_rows + dense rows,
   // sp_heads_total, D] buffer; this rank's heads are [sp_rank*heads, (sp_rank+1)*heads).
   int sp_world, sp_rank, sp_heads_total;
+  int sp_head_base;           // global head index of local head 0 (default sp_rank*heads)
   long long sp_rows;          // image rows owned per rank
   unsigned long long peer_out[8];
+  float* lse_out;             // optional [B, H, q_rows] natural-log LSE of the dense rows
   int* err_flag;
 };
 

@@ -465,7 +465,7 @@ carved_attn_v6_kernel(const __grid_constant__ CUtensorMap tm_q,
     if (p.sp_world > 0) {
       // Fused Ulysses exchange (ref xdit_ring_atten.py:206-219): see generation 2.
       const long long n_img = p.sp_rows * p.sp_world;
-      const int gh = p.sp_rank * p.heads + h;
+      const int gh = p.sp_head_base + h;
       if (q_row < n_img) {
         const int owner = static_cast<int>(q_row / p.sp_rows);
         obase = reinterpret_cast<uint16_t*>(p.peer_out[owner]);

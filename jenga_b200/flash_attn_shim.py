@@ -4,7 +4,8 @@ Shadows exactly what the reference imports:
   flash_attn.flash_attn_func                       attention_block_triton_diffres.py:15,377
   flash_attn.flash_attn_interface.flash_attn_varlen_func   hyvideo/modules/attenion.py:11,109-117;
                                                            wan/modules/attention.py:113-125
-  flash_attn.flash_attn_interface._flash_attn_forward      attenion.py:221-246 (vanilla SP only)
+  flash_attn.flash_attn_interface._flash_attn_forward      attenion.py:221-246, xdit_ring_atten.py:302-327
+                                                           (out + softmax_lse)
   flash_attn.__version__                                   attenion.py:220
 Forward only, no dropout, non-causal, head_dim 128 — the only way the Jenga paths call them;
 anything else raises instead of silently doing something different.
@@ -30,7 +31,7 @@ def _check(q, k, v, dropout_p, causal, window_size, alibi_slopes):
         raise NotImplementedError("only head_dim 128 is built")
 
 
-def _dense(q, k, v, softmax_scale, out=None):
+def _dense(q, k, v, softmax_scale, out=None, lse=None):
     """q [B,Sq,H,D], k/v [B,Sk,H,D] -> [B,Sq,H,D]"""
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
@@ -38,7 +39,7 @@ def _dense(q, k, v, softmax_scale, out=None):
         out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
     scale = D ** -0.5 if softmax_scale is None else float(softmax_scale)
     _launch(q, k, v, None, 0, (Sq + BLOCK - 1) // BLOCK, scale, 0.0, 1 << 30, Sk, Sq, Sk, out, None,
-            q.dtype)
+            q.dtype, lse_out=lse)
     return out
 
 
@@ -77,9 +78,19 @@ def flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, ma
 
 
 def _flash_attn_forward(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
-                        softcap=0.0, alibi_slopes=None, return_softmax=False, **kw):
-    """Returns (out, softmax_lse) like flash_attn 2.7+; lse is not produced by this kernel, so
-    callers that merge ring steps with it (never enabled by Jenga) get a clear error."""
-    raise NotImplementedError(
-        "_flash_attn_forward (log-sum-exp output) is only used by the vanilla SP / ring paths, "
-        "which the Jenga scripts never enable (ring_degree=1); use UlyssesCarvedAttention")
+                        softcap=0.0, alibi_slopes=None, return_softmax=False, window_size_left=-1,
+                        window_size_right=-1, **kw):
+    """flash_attn.flash_attn_interface._flash_attn_forward as hyvideo/modules/attenion.py:221-246 and
+    xdit_ring_atten.py:302-327 call it (both the >=2.7 `window_size_left/right` and the older
+    `window_size` keyword forms): returns (out, softmax_lse, S_dmask, rng_state) with
+    softmax_lse fp32 [B, H, Sq] (natural log) written by the dense class of the attention kernel."""
+    ws = window_size if window_size is not None else (-1, -1)
+    if (window_size_left, window_size_right) != (-1, -1):
+        ws = (window_size_left, window_size_right)
+    _check(q, k, v, dropout_p, causal, ws, alibi_slopes)
+    if softcap not in (0, 0.0) or return_softmax:
+        raise NotImplementedError("softcap / return_softmax are not built")
+    B, Sq, H, D = q.shape
+    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    out = _dense(q, k, v, softmax_scale, lse=lse)
+    return out, lse, None, None

@@ -134,19 +134,27 @@ class UlyssesFusedAttention:
     """Same contract as UlyssesCarvedAttention, with the exchange fused into the kernels over
     NVLink peer memory (torch symmetric memory provides the mapped pointers):
 
-      in : ONE kernel (jenga_ulysses_scatter) stores this rank's Q/K/V image rows into every
-           rank's [3, N+T, H/P, D] buffer with 16-byte peer stores — replaces three all-to-alls
-           and their .contiguous() staging copies; text rows are a local head-slice copy.
+      in : jenga_ulysses_scatter stores this rank's Q/K/V image rows into every rank's
+           [3, N+T, H/P, D] buffer with 16-byte peer stores — replaces three all-to-alls and their
+           .contiguous() staging copies; text rows are a local head-slice copy.  The rank's H/P
+           heads are processed as `groups` head sub-groups: the exchange of sub-group g+1 runs on
+           a second stream UNDER the attention of sub-group g, so only the first sub-group's
+           exchange is exposed.
       out: the attention kernel's epilogue stores each finished O row straight into the token
            owner's [n_loc+T, H, D] buffer (text rows into every rank's) — replaces the
-           all-to-all, the all-gather and the permute copies.
-    Two device-side barriers per call (after the scatter, after the attention) order the peer
-    traffic; they also make buffer reuse across layers safe on a single stream."""
+           all-to-all, the all-gather and the permute copies.  The result buffer is double
+           buffered across calls (no copy out): the tensor returned by call i stays valid until
+           call i+2 is issued on the same stream.
+    Device-side barriers (symmetric-memory signal pads) order the peer traffic: one per sub-group
+    after its exchange, one per call after the attention."""
 
-    def __init__(self, group=None, variant: str = "hyvideo"):
+    def __init__(self, group=None, variant: str = "hyvideo", groups: int | None = None):
         self.group = group if group is not None else dist.group.WORLD
         self.variant = variant
+        self.groups = groups
         self._bufs = {}
+        self._side = None
+        self._call = 0
 
     def _buffers(self, N, T, h, D, n_loc, H, dtype, dev):
         import ctypes as C
@@ -161,18 +169,31 @@ class UlyssesFusedAttention:
         except Exception:
             pass
         qkv = symm.empty((3, N + T, h, D), dtype=dtype, device=dev)
-        out = symm.empty((n_loc + T, H, D), dtype=dtype, device=dev)
         h_qkv = symm.rendezvous(qkv, self.group.group_name)
-        h_out = symm.rendezvous(out, self.group.group_name)
         p_qkv = (C.c_uint64 * P)(*[int(x) for x in h_qkv.buffer_ptrs])
-        p_out = (C.c_uint64 * P)(*[int(x) for x in h_out.buffer_ptrs])
-        self._bufs[key] = (qkv, out, h_qkv, h_out, p_qkv, p_out)
+        outs = []
+        for _ in range(2):
+            out = symm.empty((n_loc + T, H, D), dtype=dtype, device=dev)
+            h_out = symm.rendezvous(out, self.group.group_name)
+            outs.append((out, h_out, (C.c_uint64 * P)(*[int(x) for x in h_out.buffer_ptrs])))
+        self._bufs[key] = (qkv, h_qkv, p_qkv, outs)
         return self._bufs[key]
+
+    @staticmethod
+    def _n_groups(h: int, want: int | None) -> int:
+        if want:
+            if h % want:
+                raise ValueError(f"{h} heads per rank do not split into {want} groups")
+            return want
+        for g in (3, 2):
+            if h % g == 0 and h >= g:
+                return g
+        return 1
 
     def __call__(self, attn, query, key, value, *, joint_tensor_query=None, joint_tensor_key=None,
                  joint_tensor_value=None, joint_strategy="none", top_k=0, text_amp=0.0,
                  block_neighbor_list=None, p_remain_rates=0.0, cu_seqlens_q=None, cu_seqlens_kv=None,
-                 **_unused):
+                 _hooks=None, **_unused):
         import ctypes as C
         from . import _lib
         from ._lib import check, lib
@@ -181,43 +202,155 @@ class UlyssesFusedAttention:
         B, n, H, D = query.shape
         if B != 1:
             raise ValueError("the fused Ulysses path is built for batch 1 (what the pipelines run)")
+        hooks = _hooks or {}
         h = H // P
         joint = joint_tensor_query is not None
         if joint and joint_strategy != "rear":
             raise ValueError("only joint_strategy='rear' is built (attenion.py:181)")
+        if joint != (joint_tensor_key is not None) or joint != (joint_tensor_value is not None):
+            raise ValueError("joint_tensor_query/key/value must be given together")
         T = joint_tensor_query.shape[1] if joint else 0
         N = P * n
         dev, dt = query.device, query.dtype
-        qkv, out, h_qkv, h_out, p_qkv, p_out = self._buffers(N, T, h, D, n, H, dt, dev)
-        a = _lib.JengaUlyssesScatterArgs()
+        qkv, h_qkv, p_qkv, outs = self._buffers(N, T, h, D, n, H, dt, dev)
+        out, h_out, p_out = outs[self._call & 1]
+        self._call += 1
+        G = self._n_groups(h, self.groups)
+        hg = h // G
         xs = [t[0] for t in (query, key, value)]
         for t in xs:
             if t.stride(2) != 1 or t.stride(1) != D:
                 raise ValueError("q/k/v must be [1, n, H, D] views with contiguous heads")
+        a = _lib.JengaUlyssesScatterArgs()
         a.x = (C.c_void_p * 3)(*[t.data_ptr() for t in xs])
         a.x_stride_s = xs[0].stride(0)
         if joint:
             js = [t[0] for t in (joint_tensor_query, joint_tensor_key, joint_tensor_value)]
+            for t in js:
+                if t.stride(2) != 1 or t.stride(1) != D:
+                    raise ValueError("joint tensors must be [1, T, H, D] views with contiguous heads")
             a.joint = (C.c_void_p * 3)(*[t.data_ptr() for t in js])
             a.joint_stride_s = js[0].stride(0)
         a.world, a.rank, a.heads, a.head_dim, a.n_loc, a.n_text = P, r, H, D, n, T
         a.peer_qkv_host = C.addressof(p_qkv)
-        with torch.cuda.device(dev):
-            check(lib.jenga_ulysses_scatter(C.byref(a), _stream_ptr(dev)), "ulysses_scatter")
-        h_qkv.barrier(channel=0)
+        main = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side if (G > 1 or hooks) else main
+        events = []
+        if side is not main:
+            side.wait_stream(main)      # q,k,v are ready; every rank has left the previous call (its end barrier)
+        with torch.cuda.stream(side), torch.cuda.device(dev):
+            for g in range(G):
+                if "pre_scatter" in hooks:
+                    hooks["pre_scatter"](g, side)
+                a.head_begin, a.head_count = g * hg, hg
+                check(lib.jenga_ulysses_scatter(C.byref(a), _stream_ptr(dev)), "ulysses_scatter")
+                if "post_scatter" in hooks:
+                    hooks["post_scatter"](g, side)
+                h_qkv.barrier(channel=0)
+                if side is not main:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
         if cu_seqlens_q is not None:
             valid = (cu_seqlens_q[1:2].to(device=dev, dtype=torch.int32) - n) + N
             cu = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), valid,
                             torch.full((1,), N + T, dtype=torch.int32, device=dev)])
         else:
             cu = None
-        sp = dict(world=P, rank=r, heads_total=H, rows=n, peers=p_out)
-        block_sparse_attention_variant(self.variant, qkv[0][None], qkv[1][None], qkv[2][None], top_k,
-                                       cu_seqlens_q=cu, cu_seqlens_kv=cu, text_blocks=(T + BLOCK - 1) // BLOCK,
-                                       text_amp=text_amp, block_neighbor_list=block_neighbor_list,
-                                       p_remain_rates=p_remain_rates, sp_out=sp)
-        h_out.barrier(channel=0)
-        return out[None].clone()  # the symmetric buffer is overwritten by the next call
+        for g in range(G):
+            if side is not main:
+                main.wait_event(events[g])
+            sl = slice(g * hg, (g + 1) * hg)
+            sp = dict(world=P, rank=r, heads_total=H, rows=n, peers=p_out, head_base=r * h + g * hg)
+            block_sparse_attention_variant(self.variant, qkv[0][None, :, sl], qkv[1][None, :, sl], qkv[2][None, :, sl],
+                                           top_k, cu_seqlens_q=cu, cu_seqlens_kv=cu,
+                                           text_blocks=(T + BLOCK - 1) // BLOCK, text_amp=text_amp,
+                                           block_neighbor_list=block_neighbor_list,
+                                           p_remain_rates=p_remain_rates, sp_out=sp)
+            if "post_attention" in hooks:
+                # per-group completion across ranks, so the caller may drain this group's heads
+                h_out.barrier(channel=0)
+                hooks["post_attention"](g, main, out, hg)
+        if "post_attention" not in hooks:
+            h_out.barrier(channel=0)
+        return out[None]
+
+    def plan(self, heads_per_rank: int) -> tuple[int, int]:
+        """(groups, heads per group) this object will use for `heads_per_rank` heads."""
+        G = self._n_groups(heads_per_rank, self.groups)
+        return G, heads_per_rank // G
+
+
+class HostPipelinedUlysses:
+    """Sequence-parallel AttenCarve for callers whose per-rank activations live in PINNED HOST
+    memory: `hq, hk, hv` [1, n_loc+T, H, D] (this rank's token slice + the replicated text rows,
+    all heads) in, `hout` [1, n_loc+T, H, D] out.  Four streams per rank, pipelined by head
+    sub-group (the operator is independent per head):
+
+        copy-in : H2D of sub-group g+1 (strided 2-D copies)   — also runs ahead into the NEXT call
+        side    : peer-store exchange of sub-group g (jenga_ulysses_scatter) + device barrier
+        main    : selection + carved attention of sub-group g (epilogue peer-stores O rows)
+        copy-out: D2H of sub-group g-1
+
+    Results are bit-identical to UlyssesFusedAttention on device-resident tensors."""
+
+    def __init__(self, n_loc: int, T: int, H: int, D: int = 128, dtype=torch.bfloat16, device="cuda",
+                 fused: UlyssesFusedAttention | None = None):
+        from ._lib import check, lib  # noqa: F401
+        self.fused = fused or UlyssesFusedAttention()
+        self.dev = torch.device(device)
+        self.n, self.T, self.H, self.D = n_loc, T, H, D
+        P = dist.get_world_size(self.fused.group)
+        self.P, self.h = P, H // P
+        self.G, self.hg = self.fused.plan(self.h)
+        mk = lambda: torch.empty((1, n_loc + T, H, D), dtype=dtype, device=self.dev)  # noqa: E731
+        self.dq, self.dk, self.dv = mk(), mk(), mk()
+        self.s_in = torch.cuda.Stream(self.dev)
+        self.s_out = torch.cuda.Stream(self.dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(self.G)]
+        self.ev_scattered = [None] * self.G
+
+    def __call__(self, hq, hk, hv, hout, **kw):
+        from .host_pipeline import _copy2d
+        n, T, H, D, P, h, G, hg = self.n, self.T, self.H, self.D, self.P, self.h, self.G, self.hg
+        for t in (hq, hk, hv, hout):
+            if tuple(t.shape) != (1, n + T, H, D) or not t.is_contiguous() or not t.is_pinned():
+                raise ValueError("host tensors must be pinned, contiguous [1, n_loc+T, H, D]")
+        es = hq.element_size()
+        pitch, width, rows = h * D * es, hg * D * es, (n + T) * P   # rows = (token, destination rank)
+        main = torch.cuda.current_stream(self.dev)
+        self.s_in.wait_stream(main)
+        for g in range(G):
+            if self.ev_scattered[g] is not None:
+                self.s_in.wait_event(self.ev_scattered[g])   # the previous call has consumed this staging slice
+            off = g * hg * D * es
+            for dst, src in ((self.dq, hq), (self.dk, hk), (self.dv, hv)):
+                _copy2d(dst.data_ptr() + off, pitch, src.data_ptr() + off, pitch, width, rows, 0, self.s_in)
+            self.ev_in[g].record(self.s_in)
+
+        def pre_scatter(g, side):
+            side.wait_event(self.ev_in[g])
+
+        def post_scatter(g, side):
+            ev = torch.cuda.Event()
+            ev.record(side)
+            self.ev_scattered[g] = ev
+
+        def post_attention(g, main_s, out, hg_):
+            ev = torch.cuda.Event()
+            ev.record(main_s)
+            self.s_out.wait_event(ev)
+            off = g * hg * D * es
+            _copy2d(hout.data_ptr() + off, pitch, out.data_ptr() + off, pitch, width, rows, 1, self.s_out)
+
+        self.fused(None, self.dq[:, :n], self.dk[:, :n], self.dv[:, :n],
+                   joint_tensor_query=self.dq[:, n:] if T else None, joint_tensor_key=self.dk[:, n:] if T else None,
+                   joint_tensor_value=self.dv[:, n:] if T else None, joint_strategy="rear" if T else "none",
+                   _hooks=dict(pre_scatter=pre_scatter, post_scatter=post_scatter, post_attention=post_attention), **kw)
+        main.wait_stream(self.s_out)
+        return hout
 
 
 def my_parallel_attention(hybrid_seq_parallel_attn, q, k, v, img_q_len, img_kv_len, cu_seqlens_q,

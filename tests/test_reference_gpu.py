@@ -229,3 +229,32 @@ def test_dense_shims_match_installed_flash_attn():
     print(f"[fa2 parity] varlen: max {dv_max:.2e} mean {dv_mean:.2e}")
     _record(case="flash_attn_varlen_func", ours_vs_fa2_max=dv_max, ours_vs_fa2_mean=dv_mean)
     assert dv_max <= 3e-2 and dv_mean <= 2e-3
+
+
+def test_flash_attn_forward_shim_returns_lse_like_installed_flash_attn():
+    """flash_attn.flash_attn_interface._flash_attn_forward (hyvideo/modules/attenion.py:221-246,
+    xdit_ring_atten.py:302-327): (out, softmax_lse, ...) — out as above, lse within 2e-3 absolute of
+    the installed wheel's (fp32 natural-log LSE; ours comes from a base-2 running max + sum)."""
+    pytest.importorskip("flash_attn")
+    from flash_attn.flash_attn_interface import _flash_attn_forward as fa_fwd
+    from jenga_b200 import flash_attn_shim as F
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, Sq, Sk, H, D = 1, 300, 128 * 9 + 40, 3, 128
+    q = torch.randn(B, Sq, H, D, generator=g, device="cuda").bfloat16()
+    k = torch.randn(B, Sk, H, D, generator=g, device="cuda").bfloat16()
+    v = torch.randn(B, Sk, H, D, generator=g, device="cuda").bfloat16()
+    ref = fa_fwd(q, k, v, dropout_p=0.0, softmax_scale=D ** -0.5, causal=False, window_size_left=-1,
+                 window_size_right=-1, softcap=0.0, alibi_slopes=None, return_softmax=False)
+    got = F._flash_attn_forward(q, k, v, dropout_p=0.0, softmax_scale=D ** -0.5, causal=False, window_size_left=-1,
+                                window_size_right=-1, softcap=0.0, alibi_slopes=None, return_softmax=False)
+    ro, rl = ref[0], ref[1]
+    go, gl = got[0], got[1]
+    assert gl.shape == rl.shape == (B, H, Sq) and gl.dtype == torch.float32
+    truth = torch.logsumexp(torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * D ** -0.5, dim=-1)
+    print(f"\n[fa2 lse] |ours-fa2| max {(gl - rl).abs().max().item():.2e}; vs fp64: fa2 {(rl - truth).abs().max().item():.2e} "
+          f"ours {(gl - truth).abs().max().item():.2e}")
+    assert (gl.double() - truth).abs().max().item() <= 2e-3
+    assert (gl - rl).abs().max().item() <= 2e-3
+    d_max, d_mean = refutil.pair_stats(go, ro)
+    assert d_max <= 3e-2 and d_mean <= 2e-3
+
