@@ -339,6 +339,24 @@ typedef struct JengaTeaCacheArgs {
 } JengaTeaCacheArgs;
 int jenga_teacache_gate(const JengaTeaCacheArgs* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f-1, first slice) elementwise chains of the DiT blocks around the attention, one pass each.
+ * ref: hyvideo/modules/models_mul_block_gc_ha_multigpu.py:196-199,295-315,409,499-500;
+ *      modulate_layers.py:31-68; activation_layers.py ("gelu_tanh").  bf16 only; rows are
+ *      `channels` contiguous elements, `*_stride` elements apart (multiples of 8).
+ * ln_modulate:   out = bf16( layer_norm_fp32(x) * bf16(1 + scale) + shift )   — the chain the
+ *                reference runs under torch.autocast(bf16) (no affine, eps as given)
+ * gate_residual: out = bf16( x + bf16(y * gate) )
+ * gelu_tanh:     out = bf16( gelu_tanh_fp32(x) ), strided source and destination (fills the
+ *                concatenation buffer of the single-stream block in place)
+ * ---------------------------------------------------------------------------------------- */
+int jenga_ln_modulate(const void* x, int64_t x_stride, const void* scale, const void* shift, void* out,
+                      int64_t out_stride, int64_t rows, int32_t channels, float eps, void* stream);
+int jenga_gate_residual(const void* x, int64_t x_stride, const void* y, int64_t y_stride, const void* gate,
+                        void* out, int64_t out_stride, int64_t rows, int32_t channels, void* stream);
+int jenga_gelu_tanh(const void* x, int64_t x_stride, void* out, int64_t out_stride, int64_t rows,
+                    int32_t channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

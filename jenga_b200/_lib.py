@@ -155,6 +155,14 @@ def _load() -> C.CDLL:
     lib.jenga_residual_store.restype = C.c_int
     lib.jenga_teacache_gate.argtypes = [C.POINTER(JengaTeaCacheArgs), C.c_void_p]
     lib.jenga_teacache_gate.restype = C.c_int
+    lib.jenga_ln_modulate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_int64, C.c_int32, C.c_float, C.c_void_p]
+    lib.jenga_ln_modulate.restype = C.c_int
+    lib.jenga_gate_residual.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.jenga_gate_residual.restype = C.c_int
+    lib.jenga_gelu_tanh.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.jenga_gelu_tanh.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 2:

@@ -28,12 +28,14 @@ import sys
 
 import torch
 
+from . import dense as DN
 from . import hyvideo as HY
 from . import wan as WAN
 
 _HY_MODULES = ("hyvideo.modules.models_mul_block_gc_ha_multigpu",)
 _WAN_MODULES = ("wan.modules.model_mul",)
-STATS = {"hy_double": 0, "hy_single": 0, "wan_self": 0, "fallback": 0, "gather": 0}
+STATS = {"hy_double": 0, "hy_single": 0, "wan_self": 0, "fallback": 0, "gather": 0, "ln_modulate": 0,
+         "gate_residual": 0, "gelu_cat": 0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -52,10 +54,27 @@ def _carved_call(x, sa_drop_rate, curve_sel):
             and curve_sel is not None and not isinstance(curve_sel, int))
 
 
+def _ln_mod(mod, norm, x, shift, scale):
+    """modulate(norm(x), shift, scale) — one fused pass when it is the autocast-bf16 chain."""
+    if DN.ln_modulate_supported(x, norm, shift, scale):
+        STATS["ln_modulate"] += 1
+        return DN.ln_modulate(x, shift, scale, eps=norm.eps)
+    return mod.modulate(norm(x), shift=shift, scale=scale)
+
+
+def _gate_res(mod, x, y, gate):
+    """x + apply_gate(y, gate) — one fused pass for bf16 batch-1 tensors."""
+    if DN.gate_residual_supported(x, y, gate):
+        STATS["gate_residual"] += 1
+        return DN.gate_residual(x, y, gate)
+    return x + mod.apply_gate(y, gate=gate)
+
+
 def _attention_section(self, mod, img_qkv, txt_qkv, norms, freqs_cis, cu_seqlens_q, cu_seqlens_kv,
                        sa_drop_rate, txt_amp, curve_sel, p_remain_rates, txt_block_num, per_block_token,
-                       text_blocks_default):
-    """prologue -> (SP exchange | select + carved attention).  Returns attn [B, L+T, H*D]."""
+                       text_blocks_default, out=None):
+    """prologue -> (SP exchange | select + carved attention).  Returns attn [B, L+T, H*D]
+    (written into `out`, a [B, L+T, H, D] view, when given and not under SP)."""
     (wq_i, eps), (wk_i, _), (wq_t, _), (wk_t, _) = norms
     heads = self.heads_num
     L = img_qkv.shape[1]
@@ -76,7 +95,7 @@ def _attention_section(self, mod, img_qkv, txt_qkv, norms, freqs_cis, cu_seqlens
                                          p_remain_rates=p_remain_rates)
     return HY.carved_attention_from_pools(q, k, v, pools, top_k=top_k, text_blocks=txt_block_num,
                                           text_amp=txt_amp, block_neighbor_list=block_neighbor_list,
-                                          p_remain_rates=p_remain_rates, cu_seqlens_q=cu_seqlens_q)
+                                          p_remain_rates=p_remain_rates, cu_seqlens_q=cu_seqlens_q, out=out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -96,8 +115,8 @@ def _make_double_forward(orig, mod, text_blocks_default):
                         per_block_token)
         i_shift1, i_scale1, i_gate1, i_shift2, i_scale2, i_gate2 = self.img_mod(vec).chunk(6, dim=-1)
         t_shift1, t_scale1, t_gate1, t_shift2, t_scale2, t_gate2 = self.txt_mod(vec).chunk(6, dim=-1)
-        img_qkv = self.img_attn_qkv(mod.modulate(self.img_norm1(img), shift=i_shift1, scale=i_scale1))
-        txt_qkv = self.txt_attn_qkv(mod.modulate(self.txt_norm1(txt), shift=t_shift1, scale=t_scale1))
+        img_qkv = self.img_attn_qkv(_ln_mod(mod, self.img_norm1, img, i_shift1, i_scale1))
+        txt_qkv = self.txt_attn_qkv(_ln_mod(mod, self.txt_norm1, txt, t_shift1, t_scale1))
         assert cu_seqlens_q.shape[0] == 2 * img.shape[0] + 1                         # :244-246
         attn = _attention_section(self, mod, img_qkv, txt_qkv, norms, freqs_cis, cu_seqlens_q, cu_seqlens_kv,
                                   sa_drop_rate, txt_amp, curve_sel, p_remain_rates, txt_block_num,
@@ -110,12 +129,10 @@ def _make_double_forward(orig, mod, text_blocks_default):
         STATS["hy_double"] += 1
         L = img.shape[1]
         img_attn, txt_attn = attn[:, :L], attn[:, L:]
-        img = img + mod.apply_gate(self.img_attn_proj(img_attn), gate=i_gate1)
-        img = img + mod.apply_gate(self.img_mlp(mod.modulate(self.img_norm2(img), shift=i_shift2, scale=i_scale2)),
-                                   gate=i_gate2)
-        txt = txt + mod.apply_gate(self.txt_attn_proj(txt_attn), gate=t_gate1)
-        txt = txt + mod.apply_gate(self.txt_mlp(mod.modulate(self.txt_norm2(txt), shift=t_shift2, scale=t_scale2)),
-                                   gate=t_gate2)
+        img = _gate_res(mod, img, self.img_attn_proj(img_attn), i_gate1)
+        img = _gate_res(mod, img, self.img_mlp(_ln_mod(mod, self.img_norm2, img, i_shift2, i_scale2)), i_gate2)
+        txt = _gate_res(mod, txt, self.txt_attn_proj(txt_attn), t_gate1)
+        txt = _gate_res(mod, txt, self.txt_mlp(_ln_mod(mod, self.txt_norm2, txt, t_shift2, t_scale2)), t_gate2)
         return img, txt
     forward.__jenga_b200__ = True
     forward.__wrapped__ = orig
@@ -134,24 +151,40 @@ def _make_single_forward(orig, mod, text_blocks_default):
                         freqs_cis, sa_drop_rate, txt_amp, curve_sel, p_remain_rates, txt_block_num,
                         per_block_token)
         shift, scale, gate = self.modulation(vec).chunk(3, dim=-1)
-        lin1 = self.linear1(mod.modulate(self.pre_norm(x), shift=shift, scale=scale))
+        lin1 = self.linear1(_ln_mod(mod, self.pre_norm, x, shift, scale))
         C3 = 3 * self.hidden_size
         L = x.shape[1] - txt_len
         # strided views into linear1's output: no split / rearrange / cat copies (:413-441)
         img_qkv, txt_qkv = lin1[:, :L, :C3], lin1[:, L:, :C3]
         mlp = lin1[:, :, C3:]
         assert cu_seqlens_q.shape[0] == 2 * x.shape[0] + 1                           # :444-446
+        # `torch.cat((attn, self.mlp_act(mlp)), 2)` (:499) without the concatenation copy: the attention
+        # kernel writes its rows into the first `hidden` columns of linear2's input buffer and the
+        # GELU kernel writes the rest
+        act = self.mlp_act
+        fuse_cat = (isinstance(act, torch.nn.GELU) and getattr(act, "approximate", "none") == "tanh"
+                    and lin1.dtype == torch.bfloat16 and x.shape[0] == 1
+                    and not getattr(self, "hybrid_seq_parallel_attn", None))
+        cat = attn_view = None
+        if fuse_cat:
+            cat = torch.empty((x.shape[0], x.shape[1], C3 // 3 + mlp.shape[-1]), dtype=lin1.dtype, device=lin1.device)
+            attn_view = cat[:, :, :C3 // 3].unflatten(2, (self.heads_num, -1))
         attn = _attention_section(self, mod, img_qkv, txt_qkv, [norms[0], norms[1], norms[0], norms[1]],
                                   freqs_cis, cu_seqlens_q, cu_seqlens_kv, sa_drop_rate, txt_amp, curve_sel,
-                                  p_remain_rates, txt_block_num, per_block_token, text_blocks_default)
+                                  p_remain_rates, txt_block_num, per_block_token, text_blocks_default, out=attn_view)
         if attn is None:
             STATS["fallback"] += 1
             return orig(self, x, vec, txt_len, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q, max_seqlen_kv,
                         freqs_cis, sa_drop_rate, txt_amp, curve_sel, p_remain_rates, txt_block_num,
                         per_block_token)
         STATS["hy_single"] += 1
-        out = self.linear2(torch.cat((attn, self.mlp_act(mlp)), 2))
-        return x + mod.apply_gate(out, gate=gate)
+        if fuse_cat:
+            STATS["gelu_cat"] += 1
+            DN.gelu_tanh_into(mlp, cat[:, :, C3 // 3:])
+            out = self.linear2(cat)
+        else:
+            out = self.linear2(torch.cat((attn, act(mlp)), 2))
+        return _gate_res(mod, x, out, gate)
     forward.__jenga_b200__ = True
     forward.__wrapped__ = orig
     return forward

@@ -97,7 +97,7 @@ def attention_prologue(img_qkv: torch.Tensor, txt_qkv: torch.Tensor | None, head
 
 def carved_attention_from_pools(q, k, v, pools, *, top_k: int, text_blocks: int = 2, text_amp: float = 0.0,
                                 block_neighbor_list=None, p_remain_rates: float = 0.5,
-                                cu_seqlens_q=None, shape_xfuse: bool = False):
+                                cu_seqlens_q=None, shape_xfuse: bool = False, out: torch.Tensor | None = None):
     """block_sparse_attention (…triton_diffres.py:399) when the prologue already produced the
     pooled block means: select_blocks + one carved-attention launch (2 launches per layer)."""
     B, S, H, D = q.shape
@@ -111,6 +111,12 @@ def carved_attention_from_pools(q, k, v, pools, *, top_k: int, text_blocks: int 
     bits = select_blocks(qp[:, :, :n_img].contiguous() if qp.shape[2] != n_img else qp, kp, n_img=n_img, nb=nb,
                          top_k=top_k, p_threshold=p_remain_rates, text_blocks=text_blocks, nbr_bits=nbr)
     seq = cu_seqlens_q[1:2].to(device=q.device, dtype=torch.int32) if cu_seqlens_q is not None else None
-    out = torch.empty_like(q)
+    if out is None:
+        out = torch.empty_like(q)
+    elif tuple(out.shape) != (B, S, H, D) or out.dtype != q.dtype or out.stride(3) != 1 or out.stride(2) != D:
+        # e.g. the first H*D columns of the single-stream block's concatenation buffer
+        raise ValueError("out must be a [B,S,H,D] view with contiguous heads")
     _launch(q, k, v, bits, n_img, text_blocks, D ** -0.5, text_amp, n_img, S, S, S, out, seq, q.dtype)
-    return out if shape_xfuse else out.reshape(B, S, H * D)
+    if shape_xfuse:
+        return out
+    return out.reshape(B, S, H * D) if out.is_contiguous() else out.flatten(2)

@@ -106,7 +106,7 @@ def test_cabi_exports_every_declared_symbol():
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/jenga_b200.h but not exported"
     lib.jenga_abi_version.restype = ctypes.c_int
-    assert lib.jenga_abi_version() == 1
+    assert lib.jenga_abi_version() == 2
 
 
 def test_attention_call_fails_loudly_without_gpu():
