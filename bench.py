@@ -741,6 +741,19 @@ def main():
         cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "sdpa-port",
                "sample": "torch SDPA + expanded block mask (same function as --impl reference): " + sample}
 
+    ditf = None
+    if rank == 0 and world == 1 and args.dit_blocks != "none" and wl["variant"] == "hyvideo" and not args.no_gpu_reference:
+        nd, ns = (20, 40) if args.dit_blocks == "full" else (int(v_) for v_ in args.dit_blocks.split(","))
+        torch.cuda.empty_cache()
+        ditf = dit_forward_leg(wl, inp, nd, ns)
+        torch.cuda.empty_cache()
+
+    gref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        gref = gpu_reference_leg(wl, inp)
+        if "total_ms" in gref:
+            gref["speedup_of_this_operator"] = gref["total_ms"] / ms
+
     if rank == 0:
         value = flops / (ms * 1e-3) / 1e12
         launches = 4 if world == 1 else 4  # block_pool x2, select_blocks, carved_attn per step
