@@ -357,6 +357,16 @@ int jenga_gate_residual(const void* x, int64_t x_stride, const void* y, int64_t 
 int jenga_gelu_tanh(const void* x, int64_t x_stride, void* out, int64_t out_stride, int64_t rows,
                     int32_t channels, void* stream);
 
+/* (f-2) ProRes stage switch in one kernel: out = trilinear_up(latents + noise_pred*d_sigma) *
+ * (1 - sigma_next) + noise * sigma_next, fp32, NCDHW contiguous.
+ * ref: pipeline_hunyuan_video_prores.py:721-731; scheduling_flow_match_discrete.py:258-299.
+ * latents/noise_pred: [batch_channels, in_t, in_h, in_w]; noise/out: [batch_channels, out_t, out_h, out_w].
+ * d_sigma = sigmas[-1] - sigmas[i]; sigma_next = sigmas[index_for_timestep(timesteps[i+1])]. */
+int jenga_prores_switch(const float* latents, const float* noise_pred, const float* noise, float* out,
+                        int32_t batch_channels, int32_t in_t, int32_t in_h, int32_t in_w,
+                        int32_t out_t, int32_t out_h, int32_t out_w, float d_sigma, float sigma_next,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,3 +183,80 @@ extern "C" int jenga_teacache_gate(const JengaTeaCacheArgs* a, void* stream) {
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "teacache_gate launch");
 }
+
+// ------------------------------------------------------------------------------------------
+// ProRes stage switch: at the step where Jenga's progressive-resolution schedule
+// moves to the next (larger) latent grid the reference runs, on the whole latent,
+//   x0      = latents.float() + noise_pred.float() * (sigmas[-1] - sigmas[i])        scheduling_flow_match_discrete.py:258-282
+//   x0_up   = F.interpolate(x0, size=(T, H2, W2), mode="trilinear")                   pipeline_hunyuan_video_prores.py:729
+//   latents = x0_up * (1 - sigma_next) + noise.float() * sigma_next                   scheduling_flow_match_discrete.py:284-299
+// as ~8 ATen kernels.  Here it is one gather kernel over the OUTPUT grid (one thread per output
+// voxel and channel): the 8 source taps are read from latents and noise_pred directly, so x0 is
+// never materialised.  Interpolation follows ATen's upsample_trilinear3d (align_corners=False):
+// src = max(0, scale*(dst+0.5)-0.5) with scale = in/out, taps (i0, min(i0+1, in-1)), weights
+// (1-lambda, lambda), nested as t(h(w)).
+// ------------------------------------------------------------------------------------------
+namespace jenga {
+namespace {
+
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& ip, float& l0, float& l1) {
+  const float s = fmaxf(scale * (static_cast<float>(dst) + 0.5f) - 0.5f, 0.f);
+  i0 = static_cast<int>(s);
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  ip = (i0 < in_size - 1) ? 1 : 0;
+  l1 = s - static_cast<float>(i0);
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+prores_switch_kernel(const float* __restrict__ lat, const float* __restrict__ pred, const float* __restrict__ noise,
+                     float* __restrict__ out, int NC, int it, int ih, int iw, int ot, int oh, int ow,
+                     float d_sigma, float sigma_next) {
+  const long long total = static_cast<long long>(NC) * ot * oh * ow;
+  const float st = static_cast<float>(it) / static_cast<float>(ot);
+  const float sh = static_cast<float>(ih) / static_cast<float>(oh);
+  const float sw = static_cast<float>(iw) / static_cast<float>(ow);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % ow);
+    const int y = static_cast<int>((i / ow) % oh);
+    const int z = static_cast<int>((i / (static_cast<long long>(ow) * oh)) % ot);
+    const long long nc = i / (static_cast<long long>(ow) * oh * ot);
+    int t0, tp, h0, hp, w0, wp;
+    float t0l, t1l, h0l, h1l, w0l, w1l;
+    src_index(st, z, it, t0, tp, t0l, t1l);
+    src_index(sh, y, ih, h0, hp, h0l, h1l);
+    src_index(sw, x, iw, w0, wp, w0l, w1l);
+    const long long base = nc * it * ih * iw;
+    auto x0 = [&](int tt, int hh, int ww) {
+      const long long o = base + (static_cast<long long>(tt) * ih + hh) * iw + ww;
+      return __fadd_rn(__ldg(lat + o), __fmul_rn(__ldg(pred + o), d_sigma));
+    };
+    const float v =
+        t0l * (h0l * (w0l * x0(t0, h0, w0) + w1l * x0(t0, h0, w0 + wp)) +
+               h1l * (w0l * x0(t0, h0 + hp, w0) + w1l * x0(t0, h0 + hp, w0 + wp))) +
+        t1l * (h0l * (w0l * x0(t0 + tp, h0, w0) + w1l * x0(t0 + tp, h0, w0 + wp)) +
+               h1l * (w0l * x0(t0 + tp, h0 + hp, w0) + w1l * x0(t0 + tp, h0 + hp, w0 + wp)));
+    out[i] = __fadd_rn(__fmul_rn(v, 1.0f - sigma_next), __fmul_rn(__ldg(noise + i), sigma_next));
+  }
+}
+
+}  // namespace
+}  // namespace jenga
+
+extern "C" int jenga_prores_switch(const float* latents, const float* noise_pred, const float* noise, float* out,
+                                   int32_t batch_channels, int32_t in_t, int32_t in_h, int32_t in_w,
+                                   int32_t out_t, int32_t out_h, int32_t out_w, float d_sigma, float sigma_next,
+                                   void* stream) {
+  using namespace jenga;
+  if (!latents || !noise_pred || !noise || !out) return set_error(JENGA_E_INVALID, "prores_switch: null pointer");
+  if (batch_channels <= 0 || in_t <= 0 || in_h <= 0 || in_w <= 0 || out_t <= 0 || out_h <= 0 || out_w <= 0)
+    return set_error(JENGA_E_INVALID, "prores_switch: bad shape");
+  const long long total = static_cast<long long>(batch_channels) * out_t * out_h * out_w;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  prores_switch_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      latents, noise_pred, noise, out, batch_channels, in_t, in_h, in_w, out_t, out_h, out_w, d_sigma, sigma_next);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "prores_switch launch");
+}

@@ -183,6 +183,29 @@ class TeaCache:
         self.cnt += 1          # jenga_wan.py:660
 
 
+def prores_switch(latents: torch.Tensor, noise_pred: torch.Tensor, latents_noise: torch.Tensor, size,
+                  d_sigma: float, sigma_next: float) -> torch.Tensor:
+    """The latent update at a ProRes stage switch (pipeline_hunyuan_video_prores.py:721-731):
+    `predict_x0_from_xt` -> `F.interpolate(..., size=size, mode="trilinear")` -> `add_noise_to_step`
+    (scheduling_flow_match_discrete.py:258-299) in one kernel.  d_sigma = sigmas[-1] - sigmas[i],
+    sigma_next = the sigma of timesteps[i+1].  Inputs are used as fp32 (the reference casts with
+    .to(torch.float32)); returns fp32 [N, C, *size]."""
+    _require_cuda(latents, noise_pred, latents_noise)
+    lat, pred, noise = (t.to(torch.float32).contiguous() for t in (latents, noise_pred, latents_noise))
+    if lat.dim() != 5 or lat.shape != pred.shape:
+        raise ValueError("latents / noise_pred must be [N, C, T, H, W] of one shape")
+    N, Cc, it, ih, iw = lat.shape
+    ot, oh, ow = (int(v) for v in size)
+    if tuple(noise.shape) != (N, Cc, ot, oh, ow):
+        raise ValueError("latents_noise must be [N, C, *size]")
+    out = torch.empty_like(noise)
+    with torch.cuda.device(lat.device):
+        check(lib.jenga_prores_switch(lat.data_ptr(), pred.data_ptr(), noise.data_ptr(), out.data_ptr(), N * Cc,
+                                      it, ih, iw, ot, oh, ow, float(d_sigma), float(sigma_next),
+                                      _stream_ptr(lat.device)), "prores_switch")
+    return out
+
+
 class GraphedHotPath:
     """CUDA-graph capture of a whole block loop's hot path (f-2): `fn(*static_inputs)` is run once
     eagerly (warm-up), captured once, then `replay()` launches every kernel of the loop with a

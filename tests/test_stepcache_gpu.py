@@ -148,3 +148,26 @@ def test_cuda_graph_replay_of_the_hot_path_is_bit_identical():
     outs = gh.replay()
     torch.cuda.synchronize()
     assert len(outs) == 6 and all(torch.equal(a, b) for a, b in zip(outs, eager))
+
+
+@pytest.mark.parametrize("shape,size", [((1, 16, 8, 17, 30), (8, 34, 60)), ((1, 16, 32, 33, 60), (32, 45, 80)),
+                                        ((2, 4, 5, 6, 7), (5, 12, 14))])
+def test_prores_stage_switch_matches_the_reference_chain(shape, size):
+    """pipeline_hunyuan_video_prores.py:721-731 restated with the reference's own torch ops:
+    predict_x0_from_xt -> F.interpolate(trilinear) -> add_noise_to_step, all fp32."""
+    from jenga_b200.stepcache import prores_switch
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    lat = torch.randn(shape, generator=g, device="cuda").bfloat16()
+    pred = torch.randn(shape, generator=g, device="cuda").bfloat16()
+    noise = torch.randn(shape[:2] + size, generator=g, device="cuda").bfloat16()
+    sig_i, sig_last, sig_next = 0.8421, 0.0, 0.8107
+    d_sigma = sig_last - sig_i
+    x0 = lat.to(torch.float32) + pred.to(torch.float32) * d_sigma
+    up = torch.nn.functional.interpolate(x0, size=size, mode="trilinear")
+    ref = up.to(torch.float32) * (1.0 - sig_next) + noise.to(torch.float32) * sig_next
+    got = prores_switch(lat, pred, noise, size, d_sigma, sig_next)
+    assert got.dtype == torch.float32 and got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    print(f"\n[prores switch {shape}->{size}] max |diff| {err:.2e}")
+    assert err <= 2e-6 * max(1.0, ref.abs().max().item())
+
