@@ -14,6 +14,9 @@
 // Rounding points follow the reference under torch.autocast(bf16):
 // pooled means, the pooled dot products and their product with D^-1/2 are each rounded to the
 // input dtype; softmax and the cumulative sum are fp32.
+#include <cstdlib>
+#include <cstring>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -469,6 +472,88 @@ pooled_scores_kernel(const uint16_t* __restrict__ q_pool, const uint16_t* __rest
   }
 }
 
+// Tensor-core form of the pooled-score GEMM (the reference does this step with a bf16 cuBLAS
+// bmm, …triton_diffres.py:227): mma.sync m16n8k16, 16-bit operands, fp32 accumulate, same two
+// rounding points on the way out.  Legacy warp-level MMA on purpose: the whole problem is
+// 5 GFLOP (24 heads x 900 x 900 x 128) — a tcgen05/TMEM pipeline would cost more to set up than
+// the math takes.  64x64 outputs per CTA, 4 warps of 32x32.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+template <int kDtype>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (kDtype == JENGA_BF16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+template <int kDtype>
+__global__ void __launch_bounds__(128)
+pooled_scores_mma_kernel(const uint16_t* __restrict__ q_pool, const uint16_t* __restrict__ k_pool,
+                         float* __restrict__ scores, int nq, int nk_pool, int n_img) {
+  constexpr int D = 128, LD = D + 8;             // +8 halves: ldmatrix rows land in distinct banks
+  __shared__ __align__(16) uint16_t As[64 * LD];
+  __shared__ __align__(16) uint16_t Bs[64 * LD];
+  const int bh = blockIdx.z;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int i = t; i < 64 * 16; i += 128) {
+    const int row = i >> 4, chunk = i & 15;
+    uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+    if (m0 + row < nq) va = __ldg(reinterpret_cast<const uint4*>(q_pool + (static_cast<size_t>(bh) * nq + m0 + row) * D) + chunk);
+    if (n0 + row < n_img) vb = __ldg(reinterpret_cast<const uint4*>(k_pool + (static_cast<size_t>(bh) * nk_pool + n0 + row) * D) + chunk);
+    *reinterpret_cast<uint4*>(As + row * LD + chunk * 8) = va;
+    *reinterpret_cast<uint4*>(Bs + row * LD + chunk * 8) = vb;
+  }
+  __syncthreads();
+  const int wm = warp >> 1, wn = warp & 1;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  const int mat = lane >> 3, r8 = lane & 7;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    const int k0 = ks * 16;
+    uint32_t a[2][4], b[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+      ldmatrix_x4(a[mi], As + (wm * 32 + mi * 16 + r8 + (mat & 1) * 8) * LD + k0 + (mat >> 1) * 8);
+#pragma unroll
+    for (int nj = 0; nj < 2; ++nj)
+      ldmatrix_x4(b[nj], Bs + (wn * 32 + nj * 16 + r8 + (mat >> 1) * 8) * LD + k0 + (mat & 1) * 8);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int n8 = 0; n8 < 4; ++n8)
+        mma_16816<kDtype>(acc[mi][n8], a[mi], b[n8 >> 1][(n8 & 1) * 2], b[n8 >> 1][(n8 & 1) * 2 + 1]);
+  }
+  const float inv_sqrt_d = 0.08838834764831845f;  // 128^-1/2
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = m0 + wm * 32 + mi * 16 + (lane >> 2) + (e >> 1) * 8;
+        const int n = n0 + wn * 32 + n8 * 8 + (lane & 3) * 2 + (e & 1);
+        if (m < nq && n < n_img)
+          scores[(static_cast<size_t>(bh) * nq + m) * n_img + n] =
+              round_to<kDtype>(round_to<kDtype>(acc[mi][n8][e]) * inv_sqrt_d);  // ref :227
+      }
+}
+
 // 32-bit descending bitonic sort, lane L owns sorted positions [32L, 32L+32)
 __device__ __forceinline__ void warp_bitonic_desc_u32(uint32_t (&key)[32], int lane) {
 #pragma unroll
@@ -661,12 +746,22 @@ int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream) {
       return set_error(JENGA_E_WORKSPACE, "select_blocks: workspace %lld < %zu bytes", (long long)a->workspace_bytes, need);
     float* scores = static_cast<float*>(a->workspace);
     dim3 g1((a->n_img + 63) / 64, (a->nq + 63) / 64, a->batch_heads);
-    const int smem1 = 2 * 128 * 68 * 4;
-    auto k1 = a->dtype == JENGA_BF16 ? pooled_scores_kernel<JENGA_BF16> : pooled_scores_kernel<JENGA_F16>;
-    cudaError_t ce = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(pooled_scores)");
-    k1<<<g1, 256, smem1, stream>>>(static_cast<const uint16_t*>(a->q_pool), static_cast<const uint16_t*>(a->k_pool),
-                                   scores, a->nq, a->nk_pool, a->n_img, a->head_dim);
+    // JENGA_SELECT_GEMM=simt selects the fp32 SIMT GEMM whose summation order equals the fused
+    // single-kernel path bit for bit (tests); the default is the tensor-core form.
+    static const bool simt = [] { const char* e = std::getenv("JENGA_SELECT_GEMM"); return e && std::strcmp(e, "simt") == 0; }();
+    cudaError_t ce;
+    if (simt) {
+      const int smem1 = 2 * 128 * 68 * 4;
+      auto k1 = a->dtype == JENGA_BF16 ? pooled_scores_kernel<JENGA_BF16> : pooled_scores_kernel<JENGA_F16>;
+      ce = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+      if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(pooled_scores)");
+      k1<<<g1, 256, smem1, stream>>>(static_cast<const uint16_t*>(a->q_pool), static_cast<const uint16_t*>(a->k_pool),
+                                     scores, a->nq, a->nk_pool, a->n_img, a->head_dim);
+    } else {
+      auto k1 = a->dtype == JENGA_BF16 ? pooled_scores_mma_kernel<JENGA_BF16> : pooled_scores_mma_kernel<JENGA_F16>;
+      k1<<<g1, 128, 0, stream>>>(static_cast<const uint16_t*>(a->q_pool), static_cast<const uint16_t*>(a->k_pool),
+                                 scores, a->nq, a->nk_pool, a->n_img);
+    }
     SelectParams p{};
     p.nq = a->nq; p.n_img = a->n_img; p.nb = a->nb; p.words = a->mask_words; p.top_k = a->top_k;
     p.p_threshold = a->p_threshold; p.text_blocks = a->text_blocks; p.first_frame_blocks = a->first_frame_blocks;

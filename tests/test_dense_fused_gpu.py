@@ -1,6 +1,7 @@
 """f-1 (first slice): the fused elementwise chains against the reference's own ATen chains under
 torch.autocast(bf16) — hyvideo/modules/models_mul_block_gc_ha_multigpu.py:196-199,295-315,409,499-500
-with modulate_layers.py:31-68.  Tolerance: <= 1 bf16 ulp per element, >= 99.9 % bit-identical
+with modulate_layers.py:31-68.  Tolerance: <= 1 bf16 ulp per element (4e-6 absolute where the
+modulate sum cancels), >= 99.9 % bit-identical
 (gate_residual: bit-exact; the others differ from ATen only in fp32 summation order / libm tanh)."""
 import sys
 from pathlib import Path
@@ -44,8 +45,12 @@ def test_ln_modulate_matches_autocast_chain(L, C):
         got = DN.ln_modulate(x, shift, scale, eps=norm.eps)
         assert torch.equal(lin(mid), lin(ref))             # i.e. the Linear sees exactly `ref`
     mx, same = _ulp_stats(got, ref)
-    print(f"\n[ln_modulate {L}x{C}] max ulp {mx}, identical {same:.5f}")
-    assert mx <= 1 and same >= 0.999
+    # n*t1 + shift cancels for some elements: there the fp32 sum is ~1e-7 * |operands| uncertain, which
+    # is many ulps of a near-zero RESULT — bound those absolutely (operands are O(1))
+    d = (got.float() - ref.float()).abs()
+    bad = (d > torch.maximum(2.0 ** -8 * ref.float().abs(), torch.tensor(4e-6, device="cuda"))).sum().item()
+    print(f"\n[ln_modulate {L}x{C}] max ulp distance {mx}, identical {same:.5f}, beyond 1 ulp / 4e-6: {bad}")
+    assert bad == 0 and same >= 0.999
     # strided input rows (a slice of a wider tensor)
     wide = torch.zeros(1, L, C + 64, dtype=torch.bfloat16, device="cuda")
     wide[:, :, :C] = x
