@@ -395,7 +395,7 @@ def bench_setup(wl, build_inputs, dev, rank, world):
         # memory; if the rendezvous is refused on this box (no P2P), every rank agrees to use NCCL.
         ok = 1
         try:
-            st["sp"] = UlyssesFusedAttention()
+            st["sp"] = UlyssesFusedAttention(variant=wl["variant"])
             bench_step(wl, st)
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
@@ -406,7 +406,7 @@ def bench_setup(wl, build_inputs, dev, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         fused = bool(t.item())
     if not fused:
-        st["sp"] = UlyssesCarvedAttention()
+        st["sp"] = UlyssesCarvedAttention(variant=wl["variant"])
     st["mode"] = "fused peer stores" if fused else "nccl all-to-all"
     return st
 
@@ -424,13 +424,13 @@ def bench_flops(wl, st, algorithmic_flops):
 
     def attn_fn(q, k, v, **kw):
         kw.pop("shape_xfuse", None)
-        o, bits = block_sparse_attention_variant("hyvideo", q, k, v, kw.pop("top_k"), shape_xfuse=True,
+        o, bits = block_sparse_attention_variant(wl["variant"], q, k, v, kw.pop("top_k"), shape_xfuse=True,
                                                  return_mask_bits=True, **kw)
         captured["bits"] = bits
         captured["heads"] = q.shape[2]
         return o
 
-    sp = UlyssesCarvedAttention(attn_fn=attn_fn)
+    sp = UlyssesCarvedAttention(attn_fn=attn_fn, variant=wl["variant"])
     my_parallel_attention(sp, st["q"], st["k"], st["v"], st["n_loc"], st["n_loc"], st["cu"], st["cu"],
                           top_k=st["top_k"], text_amp=wl["text_amp"], block_neighbor_list=st["inp"]["nbr"],
                           p_remain_rates=wl["p_remain"])
