@@ -367,6 +367,16 @@ int jenga_prores_switch(const float* latents, const float* noise_pred, const flo
                         int32_t out_t, int32_t out_h, int32_t out_w, float d_sigma, float sigma_next,
                         void* stream);
 
+/* (f-4) the curve tables and the block adjacency generated ON THE DEVICE (one thread per voxel runs
+ * the reference's per-voxel index query, gilbert.py:12-38,68-272); bit-identical to the host tables.
+ * linear_to_hilbert / hilbert_to_linear: device int64 [t*h*w] (either may be NULL).
+ * bits: device uint32 [nb, words] packed adjacency rows (zeroed by the call), nb = ceil(t*h*w/block),
+ * the format jenga_select_blocks takes as nbr_bits. */
+int jenga_gilbert_mapping_device(int t, int h, int w, int sliced, int64_t* linear_to_hilbert,
+                                 int64_t* hilbert_to_linear, void* stream);
+int jenga_block_neighbor_bits_device(int t, int h, int w, int block, const int64_t* linear_to_hilbert,
+                                     uint32_t* bits, int32_t words, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,6 +165,11 @@ def _load() -> C.CDLL:
     lib.jenga_gelu_tanh.restype = C.c_int
     lib.jenga_prores_switch.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 7 + [C.c_float, C.c_float, C.c_void_p]
     lib.jenga_prores_switch.restype = C.c_int
+    lib.jenga_gilbert_mapping_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.jenga_gilbert_mapping_device.restype = C.c_int
+    lib.jenga_block_neighbor_bits_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                     C.c_int32, C.c_void_p]
+    lib.jenga_block_neighbor_bits_device.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 2:

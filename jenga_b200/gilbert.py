@@ -118,6 +118,35 @@ def block_neighbor_csr(t: int, h: int, w: int, block_size: int = 128, sliced: bo
     return torch.from_numpy(row_ptr), torch.from_numpy(col)
 
 
+def mapping_tensors_device(t: int, h: int, w: int, sliced: bool = False, device="cuda"):
+    """(linear_to_hilbert, hilbert_order) int64 tensors built ON `device` (no host walk, no H2D)."""
+    import torch.cuda
+    dev = torch.device(device)
+    n = t * h * w
+    l2h = torch.empty(n, dtype=torch.int64, device=dev)
+    h2l = torch.empty(n, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.jenga_gilbert_mapping_device(t, h, w, int(sliced), l2h.data_ptr(), h2l.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream), "gilbert_mapping_device")
+    return l2h, h2l
+
+
+def block_neighbor_bits_device(t: int, h: int, w: int, linear_to_hilbert: torch.Tensor, block_size: int = 128):
+    """Packed adjacency bit rows int32 [nb, ceil(nb/32)] on the device of `linear_to_hilbert` — what
+    attention.neighbour_bits() produces from the dense bool matrix, without the matrix."""
+    if not linear_to_hilbert.is_cuda or linear_to_hilbert.dtype != torch.int64 or linear_to_hilbert.numel() != t * h * w:
+        raise ValueError("linear_to_hilbert must be a CUDA int64 tensor of t*h*w entries")
+    dev = linear_to_hilbert.device
+    nb = (t * h * w + block_size - 1) // block_size
+    words = (nb + 31) // 32
+    bits = torch.empty((nb, words), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.jenga_block_neighbor_bits_device(t, h, w, block_size, linear_to_hilbert.contiguous().data_ptr(),
+                                                   bits.data_ptr(), words, torch.cuda.current_stream(dev).cuda_stream),
+              "block_neighbor_bits_device")
+    return bits
+
+
 def _not_on_the_hot_path(name):
     def f(*a, **k):
         raise NotImplementedError(f"gilbert.{name} is a plotting/experiment helper no Jenga script calls")

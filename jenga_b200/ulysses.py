@@ -180,13 +180,17 @@ class UlyssesFusedAttention:
         return self._bufs[key]
 
     @staticmethod
-    def _n_groups(h: int, want: int | None) -> int:
+    def _n_groups(h: int, want: int | None, q_blocks: int | None = None) -> int:
+        """Head sub-groups per rank.  Each sub-group is its own attention launch of
+        (h/G) * q_blocks CTAs on 148 SMs x 2 CTAs: a launch of only a few waves pays its nearly
+        empty last wave (902 CTAs = 3.05 waves run as 4), which costs more than the exposed exchange
+        saves — so sub-groups are used only while every launch stays >= 12 waves."""
         if want:
             if h % want:
                 raise ValueError(f"{h} heads per rank do not split into {want} groups")
             return want
         for g in (3, 2):
-            if h % g == 0 and h >= g:
+            if h % g == 0 and h >= g and (q_blocks is None or (h // g) * q_blocks >= 12 * 296):
                 return g
         return 1
 
@@ -215,7 +219,7 @@ class UlyssesFusedAttention:
         qkv, h_qkv, p_qkv, outs = self._buffers(N, T, h, D, n, H, dt, dev)
         out, h_out, p_out = outs[self._call & 1]
         self._call += 1
-        G = self._n_groups(h, self.groups)
+        G = self._n_groups(h, self.groups, (N + T + BLOCK - 1) // BLOCK)
         hg = h // G
         xs = [t[0] for t in (query, key, value)]
         for t in xs:
@@ -277,9 +281,10 @@ class UlyssesFusedAttention:
             h_out.barrier(channel=0)
         return out[None]
 
-    def plan(self, heads_per_rank: int) -> tuple[int, int]:
-        """(groups, heads per group) this object will use for `heads_per_rank` heads."""
-        G = self._n_groups(heads_per_rank, self.groups)
+    def plan(self, heads_per_rank: int, tokens: int | None = None) -> tuple[int, int]:
+        """(groups, heads per group) this object will use for `heads_per_rank` heads over `tokens`
+        (global sequence length incl. text) tokens."""
+        G = self._n_groups(heads_per_rank, self.groups, None if tokens is None else (tokens + BLOCK - 1) // BLOCK)
         return G, heads_per_rank // G
 
 
@@ -304,7 +309,7 @@ class HostPipelinedUlysses:
         self.n, self.T, self.H, self.D = n_loc, T, H, D
         P = dist.get_world_size(self.fused.group)
         self.P, self.h = P, H // P
-        self.G, self.hg = self.fused.plan(self.h)
+        self.G, self.hg = self.fused.plan(self.h, P * n_loc + T)
         mk = lambda: torch.empty((1, n_loc + T, H, D), dtype=dtype, device=self.dev)  # noqa: E731
         self.dq, self.dk, self.dv = mk(), mk(), mk()
         self.s_in = torch.cuda.Stream(self.dev)

@@ -36,8 +36,8 @@ full = block_sparse_attention(q, k, v, 2, cu_seqlens_q=cuf, cu_seqlens_kv=cuf, t
                               block_neighbor_list=nbr, p_remain_rates=0.3, text_blocks=2)
 torch.cuda.synchronize()
 ok = torch.equal(out[:, :n_loc], full[:, sl]) and torch.equal(out[:, n_loc:], full[:, n_img:])
-fz = UlyssesFusedAttention()
-for _ in range(2):  # twice: buffer reuse across calls
+fz = UlyssesFusedAttention(groups=2)   # head sub-group pipelining (auto would pick 1 at this toy size)
+for _ in range(3):  # three times: the result buffer is double-buffered across calls
     out2 = my_parallel_attention(fz, ql, kl, vl, n_loc, n_loc, cu, cu, top_k=2, text_amp=0.3,
                                  block_neighbor_list=nbr, p_remain_rates=0.3)
     torch.cuda.synchronize()
