@@ -38,3 +38,34 @@ ms = timeit(lambda: select_blocks(qp[:, :, :900].contiguous(), kp, n_img=900, nb
 res["select_blocks"] = (ms, 0)
 for k_, (ms, b) in res.items():
     print(f"{k_:16s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}" if b else f"{k_:16s} {ms:8.3f} ms")
+
+# ---- round 2: f-1 chains, residual cache, device gilbert (algorithmic bytes = one read + one write of the tensors)
+from jenga_b200 import dense as DN, stepcache as SC
+xs = torch.randn(1, S, 3072, device=dev).bfloat16()
+sh = torch.randn(1, 3072, device=dev).bfloat16(); sc = torch.randn(1, 3072, device=dev).bfloat16()
+res2 = {}
+ms = timeit(lambda: DN.ln_modulate(xs, sh, sc)); res2["ln_modulate"] = (ms, 2 * S * 3072 * 2)
+norm = torch.nn.LayerNorm(3072, elementwise_affine=False, eps=1e-6).to(dev)
+def eager_ln():
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        return (norm(xs) * (1 + sc.unsqueeze(1)) + sh.unsqueeze(1)).to(torch.bfloat16)
+ms = timeit(eager_ln); res2["  eager ATen chain"] = (ms, 2 * S * 3072 * 2)
+ys = torch.randn(1, S, 3072, device=dev).bfloat16()
+ms = timeit(lambda: DN.gate_residual(xs, ys, sc)); res2["gate_residual"] = (ms, 3 * S * 3072 * 2)
+ms = timeit(lambda: xs + ys * sc.unsqueeze(1)); res2["  eager ATen chain"+" "] = (ms, 3 * S * 3072 * 2)
+lin1 = torch.randn(1, S, 9216 + 12288, device=dev).bfloat16()
+cat = torch.empty(1, S, 3072 + 12288, device=dev, dtype=torch.bfloat16)
+ms = timeit(lambda: DN.gelu_tanh_into(lin1[:, :, 9216:], cat[:, :, 3072:])); res2["gelu_tanh_into"] = (ms, 2 * S * 12288 * 2)
+act = torch.nn.GELU(approximate="tanh")
+att = torch.randn(1, S, 3072, device=dev).bfloat16()
+ms = timeit(lambda: torch.cat((att, act(lin1[:, :, 9216:])), 2)); res2["  eager gelu + cat"] = (ms, 2 * S * 12288 * 2)
+ms = timeit(lambda: SC.residual_apply(xs, ys)); res2["residual_apply"] = (ms, 3 * S * 3072 * 2)
+ms = timeit(lambda: SC.residual_store(xs, ys)); res2["residual_store"] = (ms, 3 * S * 3072 * 2)
+ms = timeit(lambda: gilbert.mapping_tensors_device(32, 45, 80)); res2["gilbert tables (device)"] = (ms, 0)
+dl2h, _ = gilbert.mapping_tensors_device(32, 45, 80)
+ms = timeit(lambda: gilbert.block_neighbor_bits_device(32, 45, 80, dl2h)); res2["adjacency bits (device)"] = (ms, 0)
+import time
+t0 = time.perf_counter(); gilbert.mapping_tensors(32, 45, 80); gilbert.block_neighbor_mapping(32, 45, 80); t1 = time.perf_counter()
+print(f"host walker tables + adjacency: {(t1 - t0) * 1e3:.1f} ms")
+for k_, (ms, b) in res2.items():
+    print(f"{k_:26s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}" if b else f"{k_:26s} {ms:8.3f} ms")
