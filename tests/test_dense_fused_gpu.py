@@ -48,7 +48,7 @@ def test_ln_modulate_matches_autocast_chain(L, C):
     # n*t1 + shift cancels for some elements: there the fp32 sum is ~1e-7 * |operands| uncertain, which
     # is many ulps of a near-zero RESULT — bound those absolutely (operands are O(1))
     d = (got.float() - ref.float()).abs()
-    bad = (d > torch.maximum(2.0 ** -8 * ref.float().abs(), torch.tensor(4e-6, device="cuda"))).sum().item()
+    bad = (d > 2.0 ** -7 * ref.float().abs() + 4e-6).sum().item()   # 1 bf16 ulp is up to 2^-7 relative
     print(f"\n[ln_modulate {L}x{C}] max ulp distance {mx}, identical {same:.5f}, beyond 1 ulp / 4e-6: {bad}")
     assert bad == 0 and same >= 0.999
     # strided input rows (a slice of a wider tensor)
