@@ -583,9 +583,11 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   // (tuning switch, same results up to fp32 rounding; profiles/README.md has the comparison).
   static const int gen = [] {
     const char* e = std::getenv("JENGA_ATTN_KERNEL");
-    return (e && std::strcmp(e, "v6") == 0) ? 6 : 2;
+    if (e && std::strcmp(e, "v6") == 0) return 6;
+    if (e && std::strcmp(e, "v7") == 0) return 7;
+    return 2;
   }();
-  const int kv_box_rows = gen != 2 ? kBlock : kHalf;
+  const int kv_box_rows = gen == 6 ? kBlock : kHalf;
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;
   if ((rc = make_tile_map(&tm_q, a->q, a->dtype, a->q_rows, a->heads, a->batch, a->q_stride_b,
@@ -628,10 +630,12 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   p.o_stride_h = a->o_stride_h;
   p.err_flag = a->err_flag;
   p.lse_out = a->lse_out;
-  if (a->lse_out && gen != 2) return set_error(JENGA_E_UNSUPPORTED, "lse_out: default kernel generation only");
+  if (a->lse_out && gen == 6) return set_error(JENGA_E_UNSUPPORTED, "lse_out: not in generation 6");
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
   if (grid > 0x7fffffffll) return set_error(JENGA_E_UNSUPPORTED, "grid too large");
+  if (gen == 7)
+    return launch_carved_attn_v7(tm_q, tm_k, tm_v, p, a->batch * a->heads, a->dtype == JENGA_BF16, stream);
   if (gen == 6)
     return launch_carved_attn_v6(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
   auto kern = a->dtype == JENGA_BF16 ? carved_attn_fwd_kernel<true> : carved_attn_fwd_kernel<false>;

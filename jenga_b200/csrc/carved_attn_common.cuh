@@ -58,4 +58,7 @@ struct BlockWalker {
 // kernel generation 6 (carved_attn_v6.cu): three tiles in flight over one accumulator
 int launch_carved_attn_v6(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                           const attn::KernelParams& p, unsigned grid, bool bf16, cudaStream_t stream);
+// kernel generation 7 (carved_attn_v7.cu): two q blocks per CTA, interleaved P.V / Q.K^T issue
+int launch_carved_attn_v7(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                          const attn::KernelParams& p, int batch_heads, bool bf16, cudaStream_t stream);
 }  // namespace jenga

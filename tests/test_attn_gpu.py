@@ -147,3 +147,48 @@ def test_generation6_kernel_passes_the_same_parity_suite():
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+def test_generation7_kernel_passes_the_same_parity_suite_and_equals_generation2(tmp_path):
+    """JENGA_ATTN_KERNEL=v7 (two q blocks per CTA, P.V / Q.K^T MMAs of the two streams interleaved by
+    one issuer): same parity suite in a child process, and — each stream being generation 2's
+    arithmetic — the SAME BITS as the default generation on a carved + dense + ragged + text_amp case."""
+    import os
+    import subprocess
+    env = dict(os.environ, JENGA_ATTN_KERNEL="v7")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-q", "-x", "-m", "gpu",
+                        "-k", "not generation", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from jenga_b200.attention import carved_attention_fwd, mask_onehot_to_bits
+g = torch.Generator().manual_seed(77)
+B, H, n_img, n_txt, D = 1, 3, 11, 3, 128          # odd number of sparse AND dense blocks: one CTA has an idle stream
+S = (n_img + n_txt) * 128 - 40                       # ragged tail
+q, k, v = (torch.randn(B, S, H, D, generator=g).bfloat16().cuda() for _ in range(3))
+mask = torch.rand(B, H, n_img, n_img + n_txt, generator=g) < 0.45
+for i in range(n_img): mask[:, :, i, i] = True
+mask[..., n_img:] = True
+out = carved_attention_fwd(q, k, v, mask_onehot_to_bits(mask.cuda()), nq_sparse=n_img, nq_dense=n_txt,
+                           sm_scale=D ** -0.5, text_amp=0.37, text_block_start=n_img,
+                           kv_limit_sparse=n_img * 128 + 100, q_limit_sparse=n_img * 128 + 100,
+                           kv_limit_dense=(n_img + n_txt) * 128)
+torch.cuda.synchronize()
+torch.save(out.cpu(), sys.argv[1])
+""" % str(Path(__file__).resolve().parent.parent)
+    outs = {}
+    for gen in ("v2", "v7"):
+        f = tmp_path / f"out_{gen}.pt"
+        e = dict(os.environ)
+        e.pop("JENGA_ATTN_KERNEL", None)
+        if gen == "v7":
+            e["JENGA_ATTN_KERNEL"] = "v7"
+        rr = subprocess.run([sys.executable, "-c", code, str(f)], env=e, capture_output=True, text=True, timeout=600)
+        assert rr.returncode == 0, rr.stderr[-3000:]
+        outs[gen] = torch.load(f)
+    assert torch.isfinite(outs["v2"].float()).all()
+    assert torch.equal(outs["v2"], outs["v7"])
+
