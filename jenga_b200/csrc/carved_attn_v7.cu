@@ -16,6 +16,8 @@
 // Everything a stream does (loads in consumption order, scaled-Q re-rounding, lazy rescale,
 // partial polynomial exp2, masks, epilogue incl. the Ulysses peer stores) is generation 2's code
 // on a per-stream context; results are bit-identical to generation 2.
+#include <type_traits>
+
 #include "carved_attn_common.cuh"
 
 #ifndef JENGA_POLY_EVERY
@@ -219,116 +221,112 @@ carved_attn_v7_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
   } else if (warp == 2) {
     // =============================== tcgen05 issuer (both streams) ===============================
+    // A lone thread has to keep a 560-cycle group of 12 MMAs ahead of the tensor pipe while two busy
+    // softmax warps share its scheduler, so the issue path is straight-line code: descriptors live
+    // in registers, every offset is a compile-time constant, and the two streams follow a FIXED
+    // anti-phase schedule (stream Y runs one unit behind stream X):
+    //   per tile j:  [X.PV_a(j) | Y.QK_b(j)]  [Y.PV_a(j) | X.QK_a(j+1)]  [X.PV_b(j) | Y.QK_a(j+1)]  [Y.PV_b(j) | X.QK_b(j+1)]
+    // each bracket issued as P Q Q P Q Q P Q Q P Q Q.  Inside a stream this is generation 2's order.
     const int n0 = st[0].n_tiles, n1 = st[1].n_tiles;
     if ((n0 > 0 || n1 > 0) && elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, false, 128, kHalf);
       constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, true, 128, kHeadDim);
-      // stream-indexed state as arithmetic on `s`, so that nothing is a dynamically indexed array
+      struct SD {
+        uint64_t qd, kd[2], vd[2];
+        uint32_t tm;
+        uint64_t* bars;
+      };
       const uint32_t smem0 = smem_u32(smem);
-      auto q_desc = [&](int s) { return umma_smem_desc(smem0 + s * kStreamBytes + kOffQ, 16, 1024, UMMA_LAYOUT_SW128); };
-      auto k_desc = [&](int s, int hh) {
-        return umma_smem_desc(smem0 + s * kStreamBytes + kOffK + hh * kKVBoxBytes, 16, 1024, UMMA_LAYOUT_SW128);
+      auto make = [&](int s) {
+        SD d;
+        d.qd = umma_smem_desc(smem0 + s * kStreamBytes + kOffQ, 16, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          d.kd[hh] = umma_smem_desc(smem0 + s * kStreamBytes + kOffK + hh * kKVBoxBytes, 16, 1024, UMMA_LAYOUT_SW128);
+          d.vd[hh] = umma_smem_desc(smem0 + s * kStreamBytes + kOffV + hh * kKVSlotBytes, kKVBoxBytes, 1024, UMMA_LAYOUT_SW128);
+        }
+        d.tm = tmem_base + 256u * static_cast<uint32_t>(s);
+        d.bars = bars_all + s * 16;
+        return d;
       };
-      auto v_desc = [&](int s, int hh) {
-        return umma_smem_desc(smem0 + s * kStreamBytes + kOffV + hh * kKVSlotBytes, kKVBoxBytes, 1024, UMMA_LAYOUT_SW128);
+      const SD X = make(0), Y = make(1);
+
+      // one Q.K^T k-step / one P.V k-step, all offsets compile-time
+      auto q_step = [&](const SD& d, auto HH, auto KK) {
+        constexpr int hh = decltype(HH)::value, kk = decltype(KK)::value;
+        constexpr uint64_t qoff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kQHalfBytes) >> 4);
+        constexpr uint64_t koff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * 2 * kKVBoxBytes) >> 4);
+        umma_ss(d.tm + hh * kHalf, d.qd + qoff, d.kd[hh] + koff, idesc_qk, kk > 0 ? 1u : 0u);
       };
-      auto bar = [&](int s, int id) { return bars_all + s * 16 + id; };
-      auto tmem_of = [&](int s) { return tmem_base + 256u * static_cast<uint32_t>(s); };
-      auto q_mma = [&](uint64_t qd, uint64_t kd, uint32_t d_tmem, int kk) {
-        const uint64_t qoff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * kQHalfBytes) >> 4);
-        const uint64_t koff = static_cast<uint64_t>(((kk & 3) * 32 + (kk >> 2) * 2 * kKVBoxBytes) >> 4);
-        umma_ss(d_tmem, qd + qoff, kd + koff, idesc_qk, kk > 0 ? 1u : 0u);
+      auto p_step = [&](const SD& d, auto HH, auto KK, uint32_t acc0) {
+        constexpr int hh = decltype(HH)::value, kk = decltype(KK)::value;
+        constexpr uint64_t off = static_cast<uint64_t>((kk * 16 * 128) >> 4);
+        umma_ts(d.tm + 128, d.tm + hh * kHalf + kk * 8, d.vd[hh] + off, idesc_pv, kk > 0 ? 1u : acc0);
       };
-      auto p_mma = [&](uint64_t vd, uint32_t o_tmem, uint32_t p_tmem, int kk, bool first_of_stream) {
-        const uint64_t off = static_cast<uint64_t>((kk * 16 * 128) >> 4);
-        umma_ts(o_tmem, p_tmem + kk * 8, vd + off, idesc_pv, (!first_of_stream || kk > 0) ? 1u : 0u);
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      using I3 = std::integral_constant<int, 3>;
+      using I4 = std::integral_constant<int, 4>;
+      using I5 = std::integral_constant<int, 5>;
+      using I6 = std::integral_constant<int, 6>;
+      using I7 = std::integral_constant<int, 7>;
+      auto qk_alone = [&](const SD& d, auto HH, int tile) {
+        constexpr int hh = decltype(HH)::value;
+        mbar_wait(&d.bars[K_FULL0 + hh], tile & 1, p.err_flag);
+        tc_fence_after();
+        q_step(d, HH, I0{}); q_step(d, HH, I1{}); q_step(d, HH, I2{}); q_step(d, HH, I3{});
+        q_step(d, HH, I4{}); q_step(d, HH, I5{}); q_step(d, HH, I6{}); q_step(d, HH, I7{});
+        umma_commit(&d.bars[K_EMPTY0 + hh]);
+        umma_commit(&d.bars[S_FULL0 + hh]);
+      };
+      auto pv_alone = [&](const SD& d, auto HH, int tile) {
+        constexpr int hh = decltype(HH)::value;
+        mbar_wait(&d.bars[V_FULL0 + hh], tile & 1, p.err_flag);
+        mbar_wait(&d.bars[P_FULL0 + hh], tile & 1, p.err_flag);
+        tc_fence_after();
+        const uint32_t acc0 = (tile == 0 && hh == 0) ? 0u : 1u;
+        p_step(d, HH, I0{}, acc0); p_step(d, HH, I1{}, acc0); p_step(d, HH, I2{}, acc0); p_step(d, HH, I3{}, acc0);
+        umma_commit(&d.bars[V_EMPTY0 + hh]);
+      };
+      // [P.V of half HP, tile tp, of stream dp]  interleaved with  [Q.K^T of half HQ, tile tq, of stream dq]
+      auto pair = [&](const SD& dp, auto HP, int tp, bool p_valid, const SD& dq, auto HQ, int tq, bool q_valid) {
+        constexpr int hp = decltype(HP)::value, hq = decltype(HQ)::value;
+        if (p_valid && q_valid) {
+          mbar_wait(&dq.bars[K_FULL0 + hq], tq & 1, p.err_flag);
+          mbar_wait(&dp.bars[V_FULL0 + hp], tp & 1, p.err_flag);
+          mbar_wait(&dp.bars[P_FULL0 + hp], tp & 1, p.err_flag);
+          tc_fence_after();
+          const uint32_t acc0 = (tp == 0 && hp == 0) ? 0u : 1u;
+          p_step(dp, HP, I0{}, acc0); q_step(dq, HQ, I0{}); q_step(dq, HQ, I1{});
+          p_step(dp, HP, I1{}, acc0); q_step(dq, HQ, I2{}); q_step(dq, HQ, I3{});
+          p_step(dp, HP, I2{}, acc0); q_step(dq, HQ, I4{}); q_step(dq, HQ, I5{});
+          p_step(dp, HP, I3{}, acc0); q_step(dq, HQ, I6{}); q_step(dq, HQ, I7{});
+          umma_commit(&dp.bars[V_EMPTY0 + hp]);
+          umma_commit(&dq.bars[K_EMPTY0 + hq]);
+          umma_commit(&dq.bars[S_FULL0 + hq]);
+        } else if (p_valid) {
+          pv_alone(dp, HP, tp);
+        } else if (q_valid) {
+          qk_alone(dq, HQ, tq);
+        }
       };
 
-      int u[2] = {0, 0};
-      const int total0 = n0 > 0 ? 2 + 4 * n0 : 0, total1 = n1 > 0 ? 2 + 4 * n1 : 0;
-      bool done0 = total0 == 0, done1 = total1 == 0;
-      if (!done0) mbar_wait(bar(0, Q_READY), 0, p.err_flag);
-      if (!done1) mbar_wait(bar(1, Q_READY), 0, p.err_flag);
+      if (n0 > 0) mbar_wait(&X.bars[Q_READY], 0, p.err_flag);
+      if (n1 > 0) mbar_wait(&Y.bars[Q_READY], 0, p.err_flag);
       tc_fence_after();
-      int u0 = 0, u1 = 0;
-      (void)u;
-      auto ready = [&](int s, const Unit& un) -> bool {
-        const uint32_t par = un.tile & 1;
-        if (un.is_pv) return mbar_test(bar(s, V_FULL0 + un.hh), par) && mbar_test(bar(s, P_FULL0 + un.hh), par);
-        return mbar_test(bar(s, K_FULL0 + un.hh), par);
-      };
-      auto issue_alone = [&](int s, const Unit& un) {
-        const uint32_t tm = tmem_of(s);
-        if (un.is_pv) {
-          const uint64_t vd = v_desc(s, un.hh);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) p_mma(vd, tm + 128, tm + un.hh * kHalf, kk, un.tile == 0 && un.hh == 0);
-          umma_commit(bar(s, V_EMPTY0 + un.hh));
-        } else {
-          const uint64_t qd = q_desc(s), kd = k_desc(s, un.hh);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) q_mma(qd, kd, tm + un.hh * kHalf, kk);
-          umma_commit(bar(s, K_EMPTY0 + un.hh));
-          umma_commit(bar(s, S_FULL0 + un.hh));
-        }
-      };
-      long long spin_t0 = 0;
-      int spins = 0;
-      for (;;) {
-        // skip the Q.K^T units that belong to the non-existent tile n_tiles; detect the end
-        while (!done0) {
-          if (u0 >= total0) { done0 = true; break; }
-          const Unit un = decode(u0);
-          if (!un.is_pv && un.tile >= n0) { ++u0; continue; }
-          break;
-        }
-        while (!done1) {
-          if (u1 >= total1) { done1 = true; break; }
-          const Unit un = decode(u1);
-          if (!un.is_pv && un.tile >= n1) { ++u1; continue; }
-          break;
-        }
-        if (done0 && done1) break;
-        const Unit a0 = decode(u0), a1 = decode(u1);
-        const bool r0 = !done0 && ready(0, a0);
-        const bool r1 = !done1 && ready(1, a1);
-        if (r0 && r1 && a0.is_pv != a1.is_pv) {
-          // the point of this kernel:  P Q Q P Q Q P Q Q P Q Q  across the two streams
-          tc_fence_after();
-          const int sp = a0.is_pv ? 0 : 1, sq = sp ^ 1;
-          const Unit up = a0.is_pv ? a0 : a1, uq = a0.is_pv ? a1 : a0;
-          const bool first = up.tile == 0 && up.hh == 0;
-          const uint32_t tp = tmem_of(sp), tq = tmem_of(sq);
-          const uint64_t vd = v_desc(sp, up.hh), qd = q_desc(sq), kd = k_desc(sq, uq.hh);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            p_mma(vd, tp + 128, tp + up.hh * kHalf, i, first);
-            q_mma(qd, kd, tq + uq.hh * kHalf, 2 * i);
-            q_mma(qd, kd, tq + uq.hh * kHalf, 2 * i + 1);
-          }
-          umma_commit(bar(sp, V_EMPTY0 + up.hh));
-          umma_commit(bar(sq, K_EMPTY0 + uq.hh));
-          umma_commit(bar(sq, S_FULL0 + uq.hh));
-          ++u0;
-          ++u1;
-          spins = 0;
-        } else if (r0 || r1) {
-          // one stream only (or both at the same kind: advance the one that is behind, which puts
-          // the two streams in anti-phase for the steps that follow)
-          tc_fence_after();
-          const int s = (r0 && r1) ? (u0 <= u1 ? 0 : 1) : (r0 ? 0 : 1);
-          issue_alone(s, s == 0 ? a0 : a1);
-          if (s == 0) ++u0; else ++u1;
-          spins = 0;
-        } else {
-          __nanosleep(40);   // nothing ready: do not steal issue slots from the softmax warps of this scheduler
-          if (++spins == 1) spin_t0 = clock64();
-          if ((spins & 1023) == 0 && (clock64() - spin_t0) > (1ll << 31)) {
-            if (p.err_flag) atomicExch(p.err_flag, JENGA_DEV_WATCHDOG);
-            __threadfence_system();
-            __trap();
-          }
-        }
+      if (n0 > 0) {
+        qk_alone(X, I0{}, 0);
+        qk_alone(X, I1{}, 0);
+      }
+      if (n1 > 0) qk_alone(Y, I0{}, 0);
+      const int nmax = n0 > n1 ? n0 : n1;
+#pragma unroll 1
+      for (int j = 0; j < nmax; ++j) {
+        pair(X, I0{}, j, j < n0, Y, I1{}, j, j < n1);              // X.PV_a(j)  | Y.QK_b(j)
+        pair(Y, I0{}, j, j < n1, X, I0{}, j + 1, j + 1 < n0);      // Y.PV_a(j)  | X.QK_a(j+1)
+        pair(X, I1{}, j, j < n0, Y, I0{}, j + 1, j + 1 < n1);      // X.PV_b(j)  | Y.QK_a(j+1)
+        pair(Y, I1{}, j, j < n1, X, I1{}, j + 1, j + 1 < n0);      // Y.PV_b(j)  | X.QK_b(j+1)
       }
     }
   } else if (warp >= 4) {
