@@ -298,10 +298,21 @@ carved_attn_v7_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           mbar_wait(&dp.bars[P_FULL0 + hp], tp & 1, p.err_flag);
           tc_fence_after();
           const uint32_t acc0 = (tp == 0 && hp == 0) ? 0u : 1u;
+#if defined(JENGA_V7_ORDER) && JENGA_V7_ORDER == 1   // experiment: bursts instead of the interleave
+          p_step(dp, HP, I0{}, acc0); p_step(dp, HP, I1{}, acc0); p_step(dp, HP, I2{}, acc0); p_step(dp, HP, I3{}, acc0);
+          q_step(dq, HQ, I0{}); q_step(dq, HQ, I1{}); q_step(dq, HQ, I2{}); q_step(dq, HQ, I3{});
+          q_step(dq, HQ, I4{}); q_step(dq, HQ, I5{}); q_step(dq, HQ, I6{}); q_step(dq, HQ, I7{});
+#elif defined(JENGA_V7_ORDER) && JENGA_V7_ORDER == 2   // experiment: Q Q P
+          q_step(dq, HQ, I0{}); q_step(dq, HQ, I1{}); p_step(dp, HP, I0{}, acc0);
+          q_step(dq, HQ, I2{}); q_step(dq, HQ, I3{}); p_step(dp, HP, I1{}, acc0);
+          q_step(dq, HQ, I4{}); q_step(dq, HQ, I5{}); p_step(dp, HP, I2{}, acc0);
+          q_step(dq, HQ, I6{}); q_step(dq, HQ, I7{}); p_step(dp, HP, I3{}, acc0);
+#else
           p_step(dp, HP, I0{}, acc0); q_step(dq, HQ, I0{}); q_step(dq, HQ, I1{});
           p_step(dp, HP, I1{}, acc0); q_step(dq, HQ, I2{}); q_step(dq, HQ, I3{});
           p_step(dp, HP, I2{}, acc0); q_step(dq, HQ, I4{}); q_step(dq, HQ, I5{});
           p_step(dp, HP, I3{}, acc0); q_step(dq, HQ, I6{}); q_step(dq, HQ, I7{});
+#endif
           umma_commit(&dp.bars[V_EMPTY0 + hp]);
           umma_commit(&dq.bars[K_EMPTY0 + hq]);
           umma_commit(&dq.bars[S_FULL0 + hq]);
@@ -389,12 +400,26 @@ carved_attn_v7_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               for (int i = 0; i < kHalf; ++i)
                 if (col0 + i >= x.kv_limit) s[i] = -INFINITY;
             }
+#if defined(JENGA_V7_FAKE) && (JENGA_V7_FAKE & 2)
+            // TIMING EXPERIMENT ONLY: the running max is taken from the first half tile only
+            float mx0 = s[0], mx1 = s[1];
+            if (j == 0 && hh == 0) {
+#pragma unroll
+              for (int i = 4; i < kHalf; i += 4) {
+                mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+                mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+              }
+            } else {
+              mx0 = mx1 = -INFINITY;
+            }
+#else
             float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
             for (int i = 4; i < kHalf; i += 4) {
               mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
               mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
             }
+#endif
             const float mx = fmaf(fmaxf(mx0, mx1), c, amp);
             const float m_cand = fmaxf(m_used, mx);
             const bool need = (m_cand - m_used) > 8.0f;
@@ -424,6 +449,15 @@ carved_attn_v7_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
             for (int cc = 0; cc < kHalf; cc += 32) {
               uint32_t pk[16];
+#if defined(JENGA_V7_FAKE) && (JENGA_V7_FAKE & 1)
+              // TIMING EXPERIMENT ONLY (wrong results): half of the exponentials are skipped
+              if (cc == 32) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0x3c003c00u;
+                tmem_st16(tmem_S + (cc >> 1), pk);
+                continue;
+              }
+#endif
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const f32x2 xx = f2_fma(f2_pack(s[cc + 2 * i], s[cc + 2 * i + 1]), c2, off2);
