@@ -492,6 +492,8 @@ def main():
     ap.add_argument("--dit-blocks", default="4,8",
                     help="DiT block-stack leg: 'D,S' double,single blocks to build and time for both the "
                          "reference and this library (default 4,8 = 1/5 of a forward; 'full' = 20,40; 'none')")
+    ap.add_argument("--pv-fp8", action="store_true",
+                    help="ALSO time the opt-in FP8 P.V variant (reported under 'fp8_pv_variant'; never the headline)")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip timing the unmodified reference operator (Triton + FA2) on this GPU")
     args = ap.parse_args()
@@ -748,6 +750,30 @@ def main():
         ditf = dit_forward_leg(wl, inp, nd, ns)
         torch.cuda.empty_cache()
 
+    fp8v = None
+    if rank == 0 and world == 1 and args.pv_fp8 and wl["variant"] != "wan":
+        from jenga_b200.attention import block_sparse_attention_variant as _bsa
+        kw8 = dict(cu_seqlens_q=inp["cu"], cu_seqlens_kv=inp["cu"], text_blocks=wl["text_blocks"], text_amp=wl["text_amp"],
+                   block_neighbor_list=inp["nbr"], p_remain_rates=wl["p_remain"], first_frame_blocks=wl["first_frame"])
+        def step8():
+            return _bsa(wl["variant"], inp["q"], inp["k"], inp["v"], inp["top_k"], pv_fp8=True, **kw8)
+        for _ in range(3):
+            step8()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            o8 = step8()
+        f1.record()
+        torch.cuda.synchronize()
+        ms8 = f0.elapsed_time(f1) / args.steps
+        o16 = run_operator(wl, inp)
+        d = (o8.float() - o16.float()).abs()
+        rms = o16.float().pow(2).mean().sqrt().item()
+        fp8v = {"ms_per_step": ms8, "tflops_equivalent": flops / (ms8 * 1e-3) / 1e12, "speedup_vs_bf16_path": ms / ms8,
+                "vs_bf16_path": {"max_over_rms": d.max().item() / rms, "mean_over_rms": d.mean().item() / rms},
+                "note": "opt-in, lower precision in P.V only (e4m3 P and V, per-head V scale); includes the two V quantisation passes"}
+
     gref = None
     if rank == 0 and world == 1 and not args.no_gpu_reference:
         gref = gpu_reference_leg(wl, inp)
@@ -777,6 +803,8 @@ def main():
             line["cpu_baseline"] = cpu
         if dit:
             line["dit_loop"] = dit
+        if fp8v:
+            line["fp8_pv_variant"] = fp8v
         if ditf:
             line["dit_forward"] = ditf
         if gref:

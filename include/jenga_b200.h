@@ -141,6 +141,12 @@ typedef struct JengaAttnArgs {
    * row, what flash_attn's _flash_attn_forward returns as softmax_lse
    * (ref hyvideo/modules/attenion.py:221-246).  NULL = not written. */
   float* lse_out;
+  /* ABI 2, opt-in FP8 P.V variant: when v_fp8 != NULL the P.V product reads V from
+   * this contiguous [B, kv_rows, H, 128] e4m3 tensor (made by jenga_quantize_v_fp8, whose per-(b,h)
+   * absmax goes in v_fp8_amax [B*H] f32) and rounds P to e4m3; `v` is ignored.  bf16 q/k only.
+   * Own tolerance row (tests/test_fp8_gpu.py); never selected implicitly. */
+  const void* v_fp8;
+  const float* v_fp8_amax;
 } JengaAttnArgs;
 
 int jenga_carved_attn_fwd(const JengaAttnArgs* args, void* stream);
@@ -376,6 +382,13 @@ int jenga_gilbert_mapping_device(int t, int h, int w, int sliced, int64_t* linea
                                  int64_t* hilbert_to_linear, void* stream);
 int jenga_block_neighbor_bits_device(int t, int h, int w, int block, const int64_t* linear_to_hilbert,
                                      uint32_t* bits, int32_t words, void* stream);
+
+/* (f-3) per-head FP8 quantisation of V for the opt-in FP8 P.V variant: amax[b*H+h] = max |v[b,:,h,:]|,
+ * out[b,s,h,d] = e4m3_rn_satfinite(v * 448 / amax).  v: [B, S, H, 128] with element strides, bf16 or f16;
+ * out: contiguous [B, S, H, 128] bytes; amax: [B*H] f32 (zeroed by the call). */
+int jenga_quantize_v_fp8(const void* v, int32_t dtype, int32_t batch, int64_t rows, int32_t heads,
+                         int64_t stride_b, int64_t stride_s, int64_t stride_h, void* out_fp8, float* amax,
+                         void* stream);
 
 #ifdef __cplusplus
 }

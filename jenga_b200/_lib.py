@@ -41,6 +41,7 @@ class JengaAttnArgs(C.Structure):
         ("sp_rows", C.c_int64), ("out_peers_host", C.c_void_p),
         ("sp_head_base", C.c_int32), ("sp_head_base_valid", C.c_int32),
         ("lse_out", C.c_void_p),
+        ("v_fp8", C.c_void_p), ("v_fp8_amax", C.c_void_p),
     ]
 
 
@@ -170,6 +171,9 @@ def _load() -> C.CDLL:
     lib.jenga_block_neighbor_bits_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                      C.c_int32, C.c_void_p]
     lib.jenga_block_neighbor_bits_device.restype = C.c_int
+    lib.jenga_quantize_v_fp8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.jenga_quantize_v_fp8.restype = C.c_int
     lib.jenga_gilbert_xyz2d.argtypes = [C.c_int] * 6
     lib.jenga_gilbert_xyz2d.restype = C.c_int64
     if lib.jenga_abi_version() != 2:

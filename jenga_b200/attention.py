@@ -139,6 +139,21 @@ def block_pool(x: torch.Tensor, n_blocks: int, cast_out: torch.Tensor | None = N
     return pooled
 
 
+def quantize_v_fp8(v: torch.Tensor):
+    """Per-head e4m3 quantisation of V [B,S,H,128] for the opt-in FP8 P.V variant (C-ABI
+    jenga_quantize_v_fp8).  Returns (v8 uint8 [B,S,H,128] contiguous, amax f32 [B*H])."""
+    _require_cuda(v)
+    B, S, H, D = v.shape
+    if D != 128 or v.stride(3) != 1:
+        raise ValueError("v must be [B,S,H,128] with contiguous channels")
+    v8 = torch.empty((B, S, H, D), dtype=torch.uint8, device=v.device)
+    amax = torch.empty(B * H, dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib.jenga_quantize_v_fp8(v.data_ptr(), _dtype_code(v), B, S, H, v.stride(0), v.stride(1), v.stride(2),
+                                       v8.data_ptr(), amax.data_ptr(), _stream_ptr(v.device)), "quantize_v_fp8")
+    return v8, amax
+
+
 _NBR_CACHE: dict = {}
 # tests set this to a list to record every selection result (bit rows, nb) of calls made deep
 # inside a block forward; None (the default) costs nothing
@@ -226,7 +241,7 @@ def block_sparse_attention_variant(
     max_seqlen_q=None, max_seqlen_kv=None, text_blocks=None, text_amp: float = 0.0,
     block_neighbor_list=None, shape_xfuse: bool = False, p_remain_rates=None,
     first_frame_blocks: int = 0, return_mask_bits: bool = False, out: torch.Tensor | None = None,
-    sp_out: dict | None = None,
+    sp_out: dict | None = None, pv_fp8: bool = False,
 ):
     """AttenCarve operator, [B,S,H,D] in -> [B,S,H*D] (or [B,S,H,D] when shape_xfuse).
     Same arguments, defaults and quirks as the reference function of the same name; see the
@@ -298,15 +313,19 @@ def block_sparse_attention_variant(
         raise ValueError("out must be [B,S,H,D] in the result dtype with contiguous head_dim")
     a_out_dtype = out.dtype
     limit = S  # no cu_seqlens: seqlens = [context_size] (:336 / wan :452)
+    # pv_fp8 (opt-in): V is quantised per head to e4m3 and P.V runs on the FP8 tensor
+    # path; NOT the reference's arithmetic — its own tolerance row, never enabled implicitly
+    v8 = quantize_v_fp8(v) if pv_fp8 else None
     o = _launch(q, k, v, mask_bits, normal_blocks, text_blocks, D ** -0.5, text_amp, normal_blocks,
-                limit, limit, nb * BLOCK, out, seqlen_dev, a_out_dtype)
+                limit, limit, nb * BLOCK, out, seqlen_dev, a_out_dtype, v_fp8=v8)
     if not shape_xfuse:
         o = o.reshape(B, S, H * D)
     return (o, mask_bits) if return_mask_bits else o
 
 
 def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_block_start,
-            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype, sp_out=None, lse_out=None):
+            kv_limit_sparse, q_limit_sparse, kv_limit_dense, out, seqlen_dev, out_dtype, sp_out=None, lse_out=None,
+            v_fp8=None):
     B, Sq, H, D = q.shape
     a = JengaAttnArgs()
     a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
@@ -327,6 +346,8 @@ def _launch(q, k, v, mask_bits, nq_sparse, nq_dense, sm_scale, text_amp, text_bl
         if "head_base" in sp_out:
             a.sp_head_base, a.sp_head_base_valid = int(sp_out["head_base"]), 1
     a.lse_out = lse_out.data_ptr() if lse_out is not None else None
+    if v_fp8 is not None:
+        a.v_fp8, a.v_fp8_amax = v_fp8[0].data_ptr(), v_fp8[1].data_ptr()
     a.nq_sparse, a.nq_dense = nq_sparse, nq_dense
     a.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
     a.mask_words = mask_bits.shape[-1] if mask_bits is not None else 0

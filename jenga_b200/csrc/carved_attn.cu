@@ -91,7 +91,11 @@ static_assert(NUM_BARS * 8 + 4 <= 128, "barrier block overflow");
 // PV_h(j) — the tcgen05 pipe executes MMAs in issue order, so it overwrites S_h only after
 // PV_h(j) has consumed P_h(j).  The softmax warps therefore never wait for the tensor pipe in
 // steady state, and two co-resident CTAs per SM keep both the MUFU and the tensor pipe fed.
-template <bool kBF16>
+// kPvFp8 (opt-in): P and V enter the P.V product as FP8 e4m3 — V quantised per head by
+// jenga_quantize_v_fp8 (scale = absmax/448), P converted with cvt.rn.satfinite.e4m3x2 (p <= 2^8 by
+// the lazy-rescale bound, e4m3 max 448) — through tcgen05.mma kind::f8f6f4 (K = 32 per MMA: half the
+// P.V tensor cycles and half the V shared-memory traffic).  Q.K^T, the softmax and l stay as they are.
+template <bool kBF16, bool kPvFp8 = false>
 __global__ void __launch_bounds__(kThreads, 2)
 carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
                        const __grid_constant__ CUtensorMap tm_k,
@@ -186,9 +190,14 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
         const int row0 = blk * kBlock + hh * kHalf;
         uint8_t* dst = sV + hh * kKVSlotBytes;
         JENGA_PRODUCER_WAIT(&bars[V_EMPTY0 + hh], par, p.err_flag);
-        mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVSlotBytes);
-        tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
-        tma_load_4d(dst + kKVBoxBytes, &tm_v, &bars[V_FULL0 + hh], 64, row0, h, b);
+        if constexpr (kPvFp8) {   // 64 keys x 128 one-byte channels = one 8 KB box
+          mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVBoxBytes);
+          tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
+        } else {
+          mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVSlotBytes);
+          tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
+          tma_load_4d(dst + kKVBoxBytes, &tm_v, &bars[V_FULL0 + hh], 64, row0, h, b);
+        }
       };
       BlockWalker it(s_mask, nwords);
 #if JENGA_PRODUCER_CONSUMPTION_ORDER
@@ -255,12 +264,24 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
       auto issue_pv = [&](int hh, bool first) {
         const uint64_t v_desc =
             umma_smem_desc(smem_u32(sV + hh * kKVSlotBytes), kKVBoxBytes, 1024, UMMA_LAYOUT_SW128);
+        if constexpr (kPvFp8) {
+          // MN-major SW128 operand, one byte per channel: a key row is one 128-byte swizzle span;
+          // K = 32 keys per MMA = 32 rows = 4096 B; P advances 8 columns (4 e4m3 per column)
+          constexpr uint32_t idesc_pv8 = (1u << 4) | (1u << 16) | ((kHeadDim >> 3) << 17) | ((128u >> 4) << 24);
 #pragma unroll
-        for (int kk = 0; kk < kHalf / 16; ++kk) {
-          // 16 keys = 16 rows x 128 B inside each V box; P advances 8 packed columns
-          const uint64_t off = static_cast<uint64_t>((kk * 16 * 128) >> 4);
-          umma_ts(tmem_O, tmem_base + hh * kHalf + kk * 8, v_desc + off, idesc_pv,
-                  (!first || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kHalf / 32; ++kk) {
+            const uint64_t off = static_cast<uint64_t>((kk * 32 * 128) >> 4);
+            umma_ts_f8(tmem_O, tmem_base + hh * kHalf + kk * 8, v_desc + off, idesc_pv8,
+                       (!first || kk > 0) ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < kHalf / 16; ++kk) {
+            // 16 keys = 16 rows x 128 B inside each V box; P advances 8 packed columns
+            const uint64_t off = static_cast<uint64_t>((kk * 16 * 128) >> 4);
+            umma_ts(tmem_O, tmem_base + hh * kHalf + kk * 8, v_desc + off, idesc_pv,
+                    (!first || kk > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&bars[V_EMPTY0 + hh]);
       };
@@ -422,9 +443,22 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
                 pp = f2_pack(p0, p1);
               }
               sum2 = f2_add(sum2, pp);
-              pk[i] = pack2<kBF16>(p0, p1);
+              if constexpr (kPvFp8) {
+                // two e4m3 per cvt (low byte = first operand), four keys per 32-bit column
+                const uint32_t h16 = pack2_e4m3(p0, p1);
+                if (i & 1) pk[i >> 1] |= h16 << 16; else pk[i >> 1] = h16;
+              } else {
+                pk[i] = pack2<kBF16>(p0, p1);
+              }
             }
-            tmem_st16(tmem_S + (cc >> 1), pk);
+            if constexpr (kPvFp8) {
+              uint32_t pk8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk8[i] = pk[i];
+              tmem_st8(tmem_S + (cc >> 2), pk8);
+            } else {
+              tmem_st16(tmem_S + (cc >> 1), pk);
+            }
           }
           float sum0, sum1;
           f2_unpack(sum2, sum0, sum1);
@@ -441,7 +475,8 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     // ---- epilogue: O / l -> global (ref :135-136); rows past the limit are zeros (:156) ----
     const bool in_tensor = q_row < p.q_rows;
     const bool zero_row = (n_tiles == 0) || (!dense && q_row >= q_limit_sparse);
-    const float inv_l = zero_row ? 0.f : 1.0f / l_sum;
+    float inv_l = zero_row ? 0.f : 1.0f / l_sum;
+    if constexpr (kPvFp8) inv_l *= __ldg(p.v_fp8_amax + b * p.heads + h) * (1.0f / 448.0f);   // undo the V scale
     if (p.lse_out && dense && in_tensor) {
       // softmax_lse of flash_attn (natural log): ln sum_j exp(s_j * sm_scale) = (m + log2 l) * ln 2
       p.lse_out[(static_cast<long long>(b) * p.heads + h) * p.q_rows + q_row] =
@@ -535,6 +570,19 @@ static int make_tile_map(CUtensorMap* map, const void* base, int dtype, long lon
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+// V as FP8: contiguous [B, S, H, 128] bytes; box {128 channels, 64 keys}
+static int make_v8_map(CUtensorMap* map, const void* base, long long rows, int heads, int batch) {
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(rows),
+                              static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(batch)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(heads) * kHeadDim, static_cast<cuuint64_t>(kHeadDim),
+                                 static_cast<cuuint64_t>(rows) * heads * kHeadDim};
+  const cuuint32_t box[4] = {128, static_cast<cuuint32_t>(kHalf), 1, 1};
+  const cuuint32_t elem_strides[4] = {1, 1, 1, 1};
+  return encode_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box,
+                           elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 static bool stride_ok(long long s) { return s > 0 && (s * 2) % 16 == 0; }
 
 int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
@@ -596,8 +644,14 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   if ((rc = make_tile_map(&tm_k, a->k, a->dtype, a->kv_rows, a->heads, a->batch, a->k_stride_b,
                           a->k_stride_s, a->k_stride_h, kv_box_rows)))
     return rc;
-  if ((rc = make_tile_map(&tm_v, a->v, a->dtype, a->kv_rows, a->heads, a->batch, a->v_stride_b,
-                          a->v_stride_s, a->v_stride_h, kv_box_rows)))
+  const bool pv_fp8 = a->v_fp8 != nullptr;
+  if (pv_fp8) {
+    if (!a->v_fp8_amax || gen != 2 || a->dtype != JENGA_BF16)
+      return set_error(JENGA_E_UNSUPPORTED, "fp8 P.V: needs v_fp8_amax, bf16 q/k and the default kernel generation");
+    if (reinterpret_cast<uintptr_t>(a->v_fp8) % 16) return set_error(JENGA_E_INVALID, "v_fp8 must be 16-byte aligned");
+    if ((rc = make_v8_map(&tm_v, a->v_fp8, a->kv_rows, a->heads, a->batch))) return rc;
+  } else if ((rc = make_tile_map(&tm_v, a->v, a->dtype, a->kv_rows, a->heads, a->batch, a->v_stride_b,
+                                 a->v_stride_s, a->v_stride_h, kv_box_rows)))
     return rc;
 
   KernelParams p{};
@@ -630,6 +684,7 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   p.o_stride_h = a->o_stride_h;
   p.err_flag = a->err_flag;
   p.lse_out = a->lse_out;
+  p.v_fp8_amax = a->v_fp8_amax;
   if (a->lse_out && gen == 6) return set_error(JENGA_E_UNSUPPORTED, "lse_out: not in generation 6");
 
   const long long grid = static_cast<long long>(a->batch) * a->heads * (a->nq_sparse + a->nq_dense);
@@ -638,7 +693,8 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
     return launch_carved_attn_v7(tm_q, tm_k, tm_v, p, a->batch * a->heads, a->dtype == JENGA_BF16, stream);
   if (gen == 6)
     return launch_carved_attn_v6(tm_q, tm_k, tm_v, p, static_cast<unsigned>(grid), a->dtype == JENGA_BF16, stream);
-  auto kern = a->dtype == JENGA_BF16 ? carved_attn_fwd_kernel<true> : carved_attn_fwd_kernel<false>;
+  auto kern = pv_fp8 ? carved_attn_fwd_kernel<true, true>
+                     : (a->dtype == JENGA_BF16 ? carved_attn_fwd_kernel<true> : carved_attn_fwd_kernel<false>);
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (ce != cudaSuccess) return set_cuda_error(ce, "cudaFuncSetAttribute(carved_attn)");
   kern<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);

@@ -31,6 +31,7 @@ struct KernelParams {
   long long sp_rows;          // image rows owned per rank
   unsigned long long peer_out[8];
   float* lse_out;             // optional [B, H, q_rows] natural-log LSE of the dense rows
+  const float* v_fp8_amax;    // fp8 P.V variant: per (batch, head) absmax of V (scale = amax / 448)
   int* err_flag;
 };
 

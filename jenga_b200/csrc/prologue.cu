@@ -19,6 +19,8 @@
 // writes q,k,v once.  One CTA per 128-token block; a half-warp owns one (token, head) row
 // (8 channels per lane), so the norm reduction is 4 shuffles and each lane keeps the pooling
 // partial sums of its own 8 channels across the 128 tokens of the block.
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -138,18 +140,47 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 #endif
 constexpr int kGroup = JENGA_PRO_GROUP;
 
-template <bool kBF16>
+// ---- thread-block-cluster helpers (distributed shared memory) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_addr), "r"(rank));
+  return a;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// kSplit CTAs (one thread-block cluster) share a 128-token block, 128/kSplit tokens each: a block
+// walked by ONE CTA makes 903 uniform work items of ~370 us on 296 CTA slots — 3.05 waves that run
+// as 4 (round 1: 0.58 of the HBM peak overall, 0.76 inside full waves); with four 32-token items
+// per block the tail is a quarter as long.  The pooled block means stay deterministic: every CTA
+// keeps fp32 partial sums of its tokens, ranks 1..3 store theirs into rank 0's shared memory
+// (st.shared::cluster), and rank 0 adds them in rank order — ((p0 + p1) + p2) + p3, the order
+// block_pool_kernel uses too.
+template <bool kBF16, int kSplit>
 __global__ void __launch_bounds__(384, JENGA_PRO_MINB)
 hy_prologue_kernel(const PrologueParams p) {
   __shared__ float s_w[4][128];  // img_q, img_k, txt_q, txt_k norm weights
-  const int blk = blockIdx.x;
+  extern __shared__ float s_part[];   // [kSplit][H][2 (q,k)][128] partial sums (rank 0's copy is used)
+  constexpr int kTokPerCta = kBlock / kSplit;
+  const int blk = blockIdx.x / kSplit;
+  const int part = kSplit > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int b = blockIdx.y;
   const int S = p.L + p.T;
   const int lane16 = threadIdx.x & 15;  // 8-channel chunk inside the head row
   const int d0 = lane16 * 8;
   const int rows_per_iter = blockDim.x >> 4;  // (token, head) rows handled per pass
-  const long long tok0 = static_cast<long long>(blk) * kBlock;
-  const int n_tok = static_cast<int>(min(static_cast<long long>(kBlock), S - tok0));
+  const long long tok0 = static_cast<long long>(blk) * kBlock + part * kTokPerCta;
+  const int n_tok = static_cast<int>(max(0ll, min(static_cast<long long>(kTokPerCta), S - tok0)));
   const bool has_w = p.w_img_q != nullptr;
   if (has_w) {
     for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) {
@@ -160,10 +191,11 @@ hy_prologue_kernel(const PrologueParams p) {
     }
   }
   __syncthreads();
+  const uint32_t part_base = smem_u32(s_part);
 
   // A thread always serves the same head set {h : (h - hslot) % rows_per_iter == 0} so its
   // pooling accumulators are per (head, chunk).  With H <= rows_per_iter (24 <= 24) that is
-  // exactly one head per half-warp and the block's 128 tokens are walked sequentially.
+  // exactly one head per half-warp and the CTA's tokens are walked sequentially.
   const int hslot = threadIdx.x >> 4;
   // the two half-warps of a warp may serve different head counts: shuffle inside the half only
   const unsigned half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
@@ -171,73 +203,100 @@ hy_prologue_kernel(const PrologueParams p) {
     float qsum[8], ksum[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) qsum[i] = ksum[i] = 0.f;
-    for (int t0 = 0; t0 < n_tok; t0 += kGroup) {
-      uint4 rq[kGroup], rk[kGroup], rv[kGroup];
-      float4 rc[kGroup][2], rs[kGroup][2];  // the token's cos / sin for this thread's 8 channels
+    for (int t0 = 0; t0 < n_tok; ++t0) {
+      const long long tok = tok0 + t0;
+      const bool is_img = tok < p.L;
+      const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
+                                   : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
+      const long long sw = is_img ? p.img_sw : p.txt_sw;
+      const uint4 rq = __ldg(reinterpret_cast<const uint4*>(src));
+      const uint4 rk = __ldg(reinterpret_cast<const uint4*>(src + sw));
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
+      float4 rc[2], rs[2];
+      if (is_img && p.cos_t) {
+        const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
+        const float4* cp = reinterpret_cast<const float4*>(p.cos_t + row * 128 + d0);
+        const float4* sp = reinterpret_cast<const float4*>(p.sin_t + row * 128 + d0);
+        rc[0] = __ldg(cp);
+        rc[1] = __ldg(cp + 1);
+        rs[0] = __ldg(sp);
+        rs[1] = __ldg(sp + 1);
+      }
+      float q[8], k[8], wq[8], wk[8];
+      unpack8<kBF16>(rq, q);
+      unpack8<kBF16>(rk, k);
+      if (has_w) {
+        const float* wqs = s_w[is_img ? 0 : 2] + d0;
+        const float* wks = s_w[is_img ? 1 : 3] + d0;
 #pragma unroll
-      for (int g = 0; g < kGroup; ++g) {
-        const long long tok = tok0 + t0 + g;
-        if (t0 + g < n_tok) {
-          const bool is_img = tok < p.L;
-          const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
-                                       : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
-          const long long sw = is_img ? p.img_sw : p.txt_sw;
-          rq[g] = __ldg(reinterpret_cast<const uint4*>(src));
-          rk[g] = __ldg(reinterpret_cast<const uint4*>(src + sw));
-          rv[g] = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
-          if (is_img && p.cos_t) {
-            const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
-            const float4* cp = reinterpret_cast<const float4*>(p.cos_t + row * 128 + d0);
-            const float4* sp = reinterpret_cast<const float4*>(p.sin_t + row * 128 + d0);
-            rc[g][0] = __ldg(cp);
-            rc[g][1] = __ldg(cp + 1);
-            rs[g][0] = __ldg(sp);
-            rs[g][1] = __ldg(sp + 1);
-          }
+        for (int i = 0; i < 8; ++i) {
+          wq[i] = wqs[i];
+          wk[i] = wks[i];
         }
       }
+      const bool rotate = is_img && p.cos_t != nullptr;
+      norm_rope8<kBF16>(q, wq, has_w, p.eps, rotate, rc, rs, half_mask);
+      norm_rope8<kBF16>(k, wk, has_w, p.eps, rotate, rc, rs, half_mask);
+      const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
+      *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
+      *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
+      *reinterpret_cast<uint4*>(p.v + o) = rv;
+      // a CTA of the 4-way split owns exactly one 32-token partial sum; the one-CTA form (kSplit 1,
+      // A/B runs) sums its 128 tokens in one chain, which may differ from the split form in the last
+      // fp32 bit before the 16-bit rounding
 #pragma unroll
-      for (int g = 0; g < kGroup; ++g) {
-        const long long tok = tok0 + t0 + g;
-        if (t0 + g < n_tok) {  // uniform across the CTA
-          const bool is_img = tok < p.L;
-          float q[8], k[8], wq[8], wk[8];
-          unpack8<kBF16>(rq[g], q);
-          unpack8<kBF16>(rk[g], k);
-          if (has_w) {
-            const float* wqs = s_w[is_img ? 0 : 2] + d0;
-            const float* wks = s_w[is_img ? 1 : 3] + d0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              wq[i] = wqs[i];
-              wk[i] = wks[i];
-            }
-          }
-          const bool rotate = is_img && p.cos_t != nullptr;
-          norm_rope8<kBF16>(q, wq, has_w, p.eps, rotate, rc[g], rs[g], half_mask);
-          norm_rope8<kBF16>(k, wk, has_w, p.eps, rotate, rc[g], rs[g], half_mask);
-          const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
-          *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
-          *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
-          *reinterpret_cast<uint4*>(p.v + o) = rv[g];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            qsum[i] += q[i];
-            ksum[i] += k[i];
-          }
-        }
+      for (int i = 0; i < 8; ++i) {
+        qsum[i] += q[i];
+        ksum[i] += k[i];
       }
     }
     if (p.q_pool) {
-      float qm[8], km[8];
+      if constexpr (kSplit == 1) {
+        float qm[8], km[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        qm[i] = qsum[i] * (1.0f / kBlock);  // missing tail rows count as zeros (padding)
-        km[i] = ksum[i] * (1.0f / kBlock);
+        for (int i = 0; i < 8; ++i) {
+          qm[i] = qsum[i] * (1.0f / kBlock);  // missing tail rows count as zeros (padding)
+          km[i] = ksum[i] * (1.0f / kBlock);
+        }
+        const long long o = ((static_cast<long long>(b) * p.H + h) * p.nb + blk) * 128 + d0;
+        *reinterpret_cast<uint4*>(p.q_pool + o) = pack8<kBF16>(qm);
+        *reinterpret_cast<uint4*>(p.k_pool + o) = pack8<kBF16>(km);
+      } else {
+        // [part][h][q|k][128] floats in rank 0's shared memory
+        const uint32_t local = part_base + static_cast<uint32_t>((((part * p.H + h) * 2) * 128 + d0) * 4);
+        const uint32_t dst = map_to_rank(local, 0);
+        st_cluster_f4(dst, make_float4(qsum[0], qsum[1], qsum[2], qsum[3]));
+        st_cluster_f4(dst + 16, make_float4(qsum[4], qsum[5], qsum[6], qsum[7]));
+        st_cluster_f4(dst + 512, make_float4(ksum[0], ksum[1], ksum[2], ksum[3]));
+        st_cluster_f4(dst + 528, make_float4(ksum[4], ksum[5], ksum[6], ksum[7]));
       }
-      const long long o = ((static_cast<long long>(b) * p.H + h) * p.nb + blk) * 128 + d0;
-      *reinterpret_cast<uint4*>(p.q_pool + o) = pack8<kBF16>(qm);
-      *reinterpret_cast<uint4*>(p.k_pool + o) = pack8<kBF16>(km);
+    }
+  }
+  if constexpr (kSplit > 1) {
+    cluster_sync_all();   // every rank's partial sums have landed in rank 0's shared memory
+    if (p.q_pool && part == 0) {
+      for (int h = hslot; h < p.H; h += rows_per_iter) {
+        float qm[8], km[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qm[i] = km[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < kSplit; ++r) {
+          const float* src = s_part + (((r * p.H + h) * 2) * 128 + d0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            qm[i] = r == 0 ? src[i] : qm[i] + src[i];
+            km[i] = r == 0 ? src[128 + i] : km[i] + src[128 + i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          qm[i] *= (1.0f / kBlock);
+          km[i] *= (1.0f / kBlock);
+        }
+        const long long o = ((static_cast<long long>(b) * p.H + h) * p.nb + blk) * 128 + d0;
+        *reinterpret_cast<uint4*>(p.q_pool + o) = pack8<kBF16>(qm);
+        *reinterpret_cast<uint4*>(p.k_pool + o) = pack8<kBF16>(km);
+      }
     }
   }
 }
@@ -287,14 +346,37 @@ int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream) {
   p.k_pool = static_cast<uint16_t*>(a->k_pool);
   const long long S = a->img_tokens + a->txt_tokens;
   p.nb = static_cast<int>((S + kBlock - 1) / kBlock);
-  dim3 grid(p.nb, a->batch);
   int threads = a->heads * 16;
   if (threads > 384) threads = 384;
   threads = ((threads + 31) / 32) * 32;
+  // 4 CTAs per 128-token block (one cluster, DSMEM combine of the pooling sums); JENGA_PROLOGUE_SPLIT=1
+  // selects the one-CTA-per-block form (same results) for A/B runs
+  static const int split = [] { const char* e = std::getenv("JENGA_PROLOGUE_SPLIT"); return (e && e[0] == '1') ? 1 : 4; }();
+  const size_t part_bytes = static_cast<size_t>(4) * a->heads * 2 * 128 * sizeof(float);
+  if (split == 4 && part_bytes <= 200 * 1024) {
+    auto kern = a->dtype == JENGA_BF16 ? hy_prologue_kernel<true, 4> : hy_prologue_kernel<false, 4>;
+    cudaError_t ce0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(part_bytes));
+    if (ce0 != cudaSuccess) return set_cuda_error(ce0, "cudaFuncSetAttribute(hy_prologue)");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(p.nb) * 4u, a->batch);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = part_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ce0 = cudaLaunchKernelEx(&cfg, kern, p);
+    return ce0 == cudaSuccess ? JENGA_OK : set_cuda_error(ce0, "hy_prologue cluster launch");
+  }
+  dim3 grid(p.nb, a->batch);
   if (a->dtype == JENGA_BF16)
-    hy_prologue_kernel<true><<<grid, threads, 0, stream>>>(p);
+    hy_prologue_kernel<true, 1><<<grid, threads, 0, stream>>>(p);
   else
-    hy_prologue_kernel<false><<<grid, threads, 0, stream>>>(p);
+    hy_prologue_kernel<false, 1><<<grid, threads, 0, stream>>>(p);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? JENGA_OK : set_cuda_error(ce, "hy_prologue launch");
 }
