@@ -159,13 +159,11 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// kSplit CTAs (one thread-block cluster) share a 128-token block, 128/kSplit tokens each: a block
-// walked by ONE CTA makes 903 uniform work items of ~370 us on 296 CTA slots — 3.05 waves that run
-// as 4 (round 1: 0.58 of the HBM peak overall, 0.76 inside full waves); with four 32-token items
-// per block the tail is a quarter as long.  The pooled block means stay deterministic: every CTA
-// keeps fp32 partial sums of its tokens, ranks 1..3 store theirs into rank 0's shared memory
-// (st.shared::cluster), and rank 0 adds them in rank order — ((p0 + p1) + p2) + p3, the order
-// block_pool_kernel uses too.
+// kSplit == 1 (default): one CTA walks a 128-token block.  kSplit == 4 (experiment, see the launcher):
+// a thread-block cluster shares the block, 32 tokens per CTA, to shorten the last wave (903 uniform
+// work items on 296 CTA slots are 3.05 waves that run as 4); every CTA keeps fp32 partial sums of its
+// tokens, ranks 1..3 store theirs into rank 0's shared memory (st.shared::cluster) and rank 0 adds
+// them in rank order, so the pooled means stay deterministic.
 template <bool kBF16, int kSplit>
 __global__ void __launch_bounds__(384, JENGA_PRO_MINB)
 hy_prologue_kernel(const PrologueParams p) {
@@ -349,9 +347,13 @@ int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream) {
   int threads = a->heads * 16;
   if (threads > 384) threads = 384;
   threads = ((threads + 31) / 32) * 32;
-  // 4 CTAs per 128-token block (one cluster, DSMEM combine of the pooling sums); JENGA_PROLOGUE_SPLIT=1
-  // selects the one-CTA-per-block form (same results) for A/B runs
-  static const int split = [] { const char* e = std::getenv("JENGA_PROLOGUE_SPLIT"); return (e && e[0] == '1') ? 1 : 4; }();
+  // Default: one CTA per 128-token block.  JENGA_PROLOGUE_SPLIT=4 selects the experimental form with
+  // 4 CTAs per block (one thread-block cluster, DSMEM combine of the pooling sums).  Measured at
+  // HY-720p (profiles/README.md): 1.55 ms vs 1.12 ms — the 96 KB of partial-sum shared memory per CTA
+  // leaves the 24 heads of a token no L1 to share their cos/sin row in, and that costs more than the
+  // shorter last wave saves.  Its pooled means may differ from the default's in the last fp32 bit
+  // before the 16-bit rounding (4 x 32-token partial sums instead of one 128-token chain).
+  static const int split = [] { const char* e = std::getenv("JENGA_PROLOGUE_SPLIT"); return (e && e[0] == '4') ? 4 : 1; }();
   const size_t part_bytes = static_cast<size_t>(4) * a->heads * 2 * 128 * sizeof(float);
   if (split == 4 && part_bytes <= 200 * 1024) {
     auto kern = a->dtype == JENGA_BF16 ? hy_prologue_kernel<true, 4> : hy_prologue_kernel<false, 4>;

@@ -76,20 +76,9 @@ block_pool_kernel(const void* __restrict__ x, uint16_t* __restrict__ pooled,
   for (int vidx = threadIdx.x; vidx < vecs; vidx += blockDim.x) {
     const int h = vidx / vec_per_head;
     const int d0 = (vidx - h * vec_per_head) * 8;
-    // sums are closed every 32 rows — ((p0 + p1) + p2) + p3 — the order hy_prologue_kernel's four
-    // cluster ranks produce, so that both kernels emit bit-identical pooled means
-    float acc[8], part[8];
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = part[i] = 0.f;
-    auto close = [&](int r) {
-      if (((r + 1) & 31) == 0 || r + 1 == n_rows) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[i] += part[i];
-          part[i] = 0.f;
-        }
-      }
-    };
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     if constexpr (kIn == JENGA_F32) {
       const float* base = static_cast<const float*>(x) + b * sb + h * sh + d0;
 #pragma unroll 4
@@ -101,7 +90,7 @@ block_pool_kernel(const void* __restrict__ x, uint16_t* __restrict__ pooled,
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           o16[i] = to_bits16<kOut>(f[i]);
-          part[i] += from_bits16<kOut>(o16[i]);
+          acc[i] += from_bits16<kOut>(o16[i]);
         }
         if (cast_out) {
           uint4 v;
@@ -112,7 +101,6 @@ block_pool_kernel(const void* __restrict__ x, uint16_t* __restrict__ pooled,
           *reinterpret_cast<uint4*>(cast_out + ((static_cast<long long>(b) * rows + row0 + r) * heads + h) *
                                                    head_dim + d0) = v;
         }
-        close(r);
       }
     } else {
       const uint16_t* base = static_cast<const uint16_t*>(x) + b * sb + h * sh + d0;
@@ -122,10 +110,9 @@ block_pool_kernel(const void* __restrict__ x, uint16_t* __restrict__ pooled,
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          part[2 * i] += from_bits16<kIn>(static_cast<uint16_t>(w[i] & 0xffffu));
-          part[2 * i + 1] += from_bits16<kIn>(static_cast<uint16_t>(w[i] >> 16));
+          acc[2 * i] += from_bits16<kIn>(static_cast<uint16_t>(w[i] & 0xffffu));
+          acc[2 * i + 1] += from_bits16<kIn>(static_cast<uint16_t>(w[i] >> 16));
         }
-        close(r);
       }
     }
     uint16_t o16[8];
