@@ -782,7 +782,9 @@ def main():
 
     if rank == 0:
         value = flops / (ms * 1e-3) / 1e12
-        launches = 4 if world == 1 else 4  # block_pool x2, select_blocks, carved_attn per step
+        # our kernels per step: block_pool x2, pooled_scores_mma, select_rows, carved_attn (+ ulysses_scatter
+        # and the same per head sub-group under Ulysses)
+        launches = 5 if world == 1 else 1 + 5
         line = {
             "metric": metric, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
