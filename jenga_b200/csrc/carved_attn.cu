@@ -636,6 +636,12 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
     return 2;
   }();
   const int kv_box_rows = gen == 6 ? kBlock : kHalf;
+  const bool pv_fp8 = a->v_fp8 != nullptr;
+  if (pv_fp8) {
+    if (!a->v_fp8_amax || gen != 2 || a->dtype != JENGA_BF16)
+      return set_error(JENGA_E_UNSUPPORTED, "fp8 P.V: needs v_fp8_amax, bf16 q/k and the default kernel generation");
+    if (reinterpret_cast<uintptr_t>(a->v_fp8) % 16) return set_error(JENGA_E_INVALID, "v_fp8 must be 16-byte aligned");
+  }
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;
   if ((rc = make_tile_map(&tm_q, a->q, a->dtype, a->q_rows, a->heads, a->batch, a->q_stride_b,
@@ -644,11 +650,7 @@ int carved_attn_fwd_impl(const JengaAttnArgs* a, cudaStream_t stream) {
   if ((rc = make_tile_map(&tm_k, a->k, a->dtype, a->kv_rows, a->heads, a->batch, a->k_stride_b,
                           a->k_stride_s, a->k_stride_h, kv_box_rows)))
     return rc;
-  const bool pv_fp8 = a->v_fp8 != nullptr;
   if (pv_fp8) {
-    if (!a->v_fp8_amax || gen != 2 || a->dtype != JENGA_BF16)
-      return set_error(JENGA_E_UNSUPPORTED, "fp8 P.V: needs v_fp8_amax, bf16 q/k and the default kernel generation");
-    if (reinterpret_cast<uintptr_t>(a->v_fp8) % 16) return set_error(JENGA_E_INVALID, "v_fp8 must be 16-byte aligned");
     if ((rc = make_v8_map(&tm_v, a->v_fp8, a->kv_rows, a->heads, a->batch))) return rc;
   } else if ((rc = make_tile_map(&tm_v, a->v, a->dtype, a->kv_rows, a->heads, a->batch, a->v_stride_b,
                                  a->v_stride_s, a->v_stride_h, kv_box_rows)))

@@ -142,3 +142,64 @@ def test_wan_prologue_and_ulysses_scatter_validation():
 
     s = JengaUlyssesScatterArgs()
     assert lib.jenga_ulysses_scatter(C.byref(s), None) == E_INVALID and "null" in _err()
+
+
+# ------------------------------------------------------------------ round-2 entry points
+def test_round2_entry_points_validate_before_touching_cuda():
+    """step cache, dense chains, FP8 quantisation, ProRes switch, device gilbert: bad arguments are
+    rejected with a negative code and a message (no CUDA call is reached)."""
+    P = 0x10000   # never dereferenced on the validation paths
+    cases = [
+        (lambda: lib.jenga_residual_apply(None, P, 16, _lib.JENGA_BF16, None), E_INVALID, "null"),
+        (lambda: lib.jenga_residual_apply(P, P, 16, 7, None), E_INVALID, "dtype"),
+        (lambda: lib.jenga_residual_apply(P + 8, P, 16, _lib.JENGA_BF16, None), E_INVALID, "aligned"),
+        (lambda: lib.jenga_residual_store(P, P, None, 16, _lib.JENGA_F32, None), E_INVALID, "null"),
+        (lambda: lib.jenga_ln_modulate(P, 3072, P, P, P, 3072, 10, 3070, 1e-6, None), E_INVALID, "multiples of 8"),
+        (lambda: lib.jenga_ln_modulate(P, 3072, None, P, P, 3072, 10, 3072, 1e-6, None), E_INVALID, "null"),
+        (lambda: lib.jenga_ln_modulate(P, 8192, P, P, P, 8192, 10, 8192, 1e-6, None), E_UNSUPPORTED, "6144"),
+        (lambda: lib.jenga_gate_residual(P, 64, P, 64, P, P, 64, 0, 64, None), E_INVALID, "shape"),
+        (lambda: lib.jenga_gelu_tanh(P, 64, P + 2, 64, 4, 64, None), E_INVALID, "aligned"),
+        (lambda: lib.jenga_quantize_v_fp8(P, _lib.JENGA_F32, 1, 128, 2, 128 * 256, 256, 128, P, P, None), E_INVALID, "dtype"),
+        (lambda: lib.jenga_quantize_v_fp8(P, _lib.JENGA_BF16, 1, 128, 2, 128 * 256, 250, 128, P, P, None), E_INVALID, "alignment"),
+        (lambda: lib.jenga_prores_switch(P, P, None, P, 16, 4, 4, 4, 4, 8, 8, 0.1, 0.5, None), E_INVALID, "null"),
+        (lambda: lib.jenga_prores_switch(P, P, P, P, 16, 4, 0, 4, 4, 8, 8, 0.1, 0.5, None), E_INVALID, "shape"),
+        (lambda: lib.jenga_gilbert_mapping_device(0, 4, 4, 0, P, P, None), E_INVALID, "empty"),
+        (lambda: lib.jenga_gilbert_mapping_device(2, 4, 4, 0, None, None, None), E_INVALID, "no output"),
+        (lambda: lib.jenga_block_neighbor_bits_device(2, 4, 4, 128, P, P, 0, None), E_INVALID, "words"),
+    ]
+    for fn, code, needle in cases:
+        rc = fn()
+        assert rc == code, (rc, _err())
+        assert needle.lower() in _err().lower(), (needle, _err())
+    a = _lib.JengaTeaCacheArgs()
+    assert lib.jenga_teacache_gate(C.byref(a), None) == E_INVALID and "null" in _err()
+    a.cur = a.prev = a.state = a.flag = P
+    a.n, a.n_coeff, a.dtype = 100, 9, _lib.JENGA_F32
+    assert lib.jenga_teacache_gate(C.byref(a), None) == E_INVALID and "sizes" in _err()
+    a.n_coeff, a.dtype = 5, _lib.JENGA_BF16
+    assert lib.jenga_teacache_gate(C.byref(a), None) == E_UNSUPPORTED and "f32" in _err()
+
+
+def test_fp8_and_head_group_arguments_of_the_attention_entry_point():
+    """ABI 2 fields: the FP8 P.V variant needs its amax array, bf16 and the default generation; a
+    Ulysses head sub-group must lie inside sp_heads_total."""
+    a = _attn_args(v_fp8=0x20000)
+    assert lib.jenga_carved_attn_fwd(C.byref(a), None) == E_UNSUPPORTED and "fp8" in _err().lower()
+    a = _attn_args(v_fp8=0x20000, v_fp8_amax=0x30000, dtype=_lib.JENGA_F16, out_dtype=_lib.JENGA_F16)
+    assert lib.jenga_carved_attn_fwd(C.byref(a), None) == E_UNSUPPORTED
+    peers = (C.c_uint64 * 2)(0x40000, 0x50000)
+    a = _attn_args(sp_world=2, sp_rank=1, sp_heads_total=4, sp_rows=128, out_peers_host=C.addressof(peers),
+                   sp_head_base=3, sp_head_base_valid=1)       # heads [3, 5) of 4
+    assert lib.jenga_carved_attn_fwd(C.byref(a), None) == E_INVALID and "head range" in _err()
+
+
+def test_scatter_head_group_validation():
+    a = _lib.JengaUlyssesScatterArgs()
+    P = 0x10000
+    a.x = (C.c_void_p * 3)(P, P, P)
+    a.x_stride_s = 4 * 128
+    a.world, a.rank, a.heads, a.head_dim, a.n_loc, a.n_text = 2, 0, 4, 128, 128, 0
+    peers = (C.c_uint64 * 2)(P, P)
+    a.peer_qkv_host = C.addressof(peers)
+    a.head_begin, a.head_count = 1, 2                           # local heads [1, 3) of 2
+    assert lib.jenga_ulysses_scatter(C.byref(a), None) == E_INVALID and "head group" in _err()
