@@ -331,8 +331,13 @@ class HostPipelinedUlysses:
             if self.ev_scattered[g] is not None:
                 self.s_in.wait_event(self.ev_scattered[g])   # the previous call has consumed this staging slice
             off = g * hg * D * es
-            for dst, src in ((self.dq, hq), (self.dk, hk), (self.dv, hv)):
-                _copy2d(dst.data_ptr() + off, pitch, src.data_ptr() + off, pitch, width, rows, 0, self.s_in)
+            if G == 1:      # the whole slice is one contiguous copy
+                with torch.cuda.stream(self.s_in):
+                    for dst, src in ((self.dq, hq), (self.dk, hk), (self.dv, hv)):
+                        dst.copy_(src, non_blocking=True)
+            else:
+                for dst, src in ((self.dq, hq), (self.dk, hk), (self.dv, hv)):
+                    _copy2d(dst.data_ptr() + off, pitch, src.data_ptr() + off, pitch, width, rows, 0, self.s_in)
             self.ev_in[g].record(self.s_in)
 
         def pre_scatter(g, side):
@@ -348,7 +353,11 @@ class HostPipelinedUlysses:
             ev.record(main_s)
             self.s_out.wait_event(ev)
             off = g * hg * D * es
-            _copy2d(hout.data_ptr() + off, pitch, out.data_ptr() + off, pitch, width, rows, 1, self.s_out)
+            if G == 1:
+                with torch.cuda.stream(self.s_out):
+                    hout.copy_(out.view(hout.shape), non_blocking=True)
+            else:
+                _copy2d(hout.data_ptr() + off, pitch, out.data_ptr() + off, pitch, width, rows, 1, self.s_out)
 
         self.fused(None, self.dq[:, :n], self.dk[:, :n], self.dv[:, :n],
                    joint_tensor_query=self.dq[:, n:] if T else None, joint_tensor_key=self.dk[:, n:] if T else None,
