@@ -165,8 +165,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 // tokens, ranks 1..3 store theirs into rank 0's shared memory (st.shared::cluster) and rank 0 adds
 // them in rank order, so the pooled means stay deterministic.
 template <bool kBF16, int kSplit>
-__global__ void __launch_bounds__(384, JENGA_PRO_MINB)
+__global__ void __launch_bounds__(384, (kSplit == 1 ? JENGA_PRO_MINB : 2))
 hy_prologue_kernel(const PrologueParams p) {
+  constexpr int kGroup = kSplit == 1 ? JENGA_PRO_GROUP : 1;
   __shared__ float s_w[4][128];  // img_q, img_k, txt_q, txt_k norm weights
   extern __shared__ float s_part[];   // [kSplit][H][2 (q,k)][128] partial sums (rank 0's copy is used)
   constexpr int kTokPerCta = kBlock / kSplit;
@@ -201,51 +202,63 @@ hy_prologue_kernel(const PrologueParams p) {
     float qsum[8], ksum[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) qsum[i] = ksum[i] = 0.f;
-    for (int t0 = 0; t0 < n_tok; ++t0) {
-      const long long tok = tok0 + t0;
-      const bool is_img = tok < p.L;
-      const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
-                                   : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
-      const long long sw = is_img ? p.img_sw : p.txt_sw;
-      const uint4 rq = __ldg(reinterpret_cast<const uint4*>(src));
-      const uint4 rk = __ldg(reinterpret_cast<const uint4*>(src + sw));
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
-      float4 rc[2], rs[2];
-      if (is_img && p.cos_t) {
-        const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
-        const float4* cp = reinterpret_cast<const float4*>(p.cos_t + row * 128 + d0);
-        const float4* sp = reinterpret_cast<const float4*>(p.sin_t + row * 128 + d0);
-        rc[0] = __ldg(cp);
-        rc[1] = __ldg(cp + 1);
-        rs[0] = __ldg(sp);
-        rs[1] = __ldg(sp + 1);
-      }
-      float q[8], k[8], wq[8], wk[8];
-      unpack8<kBF16>(rq, q);
-      unpack8<kBF16>(rk, k);
-      if (has_w) {
-        const float* wqs = s_w[is_img ? 0 : 2] + d0;
-        const float* wks = s_w[is_img ? 1 : 3] + d0;
+    for (int t0 = 0; t0 < n_tok; t0 += kGroup) {
+      // all of a group's loads are issued before any arithmetic: the kernel is a pure stream, what
+      // matters is bytes in flight per SM (~1.7 us of HBM latency x 44 GB/s per SM ~ 75 KB)
+      uint4 rq[kGroup], rk[kGroup], rv[kGroup];
+      float4 rc[kGroup][2], rs[kGroup][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          wq[i] = wqs[i];
-          wk[i] = wks[i];
+      for (int g = 0; g < kGroup; ++g) {
+        const long long tok = tok0 + t0 + g;
+        if (t0 + g < n_tok) {
+          const bool is_img = tok < p.L;
+          const uint16_t* src = is_img ? p.img + b * p.img_sb + tok * p.img_ss + h * p.img_sh + d0
+                                       : p.txt + b * p.txt_sb + (tok - p.L) * p.txt_ss + h * p.txt_sh + d0;
+          const long long sw = is_img ? p.img_sw : p.txt_sw;
+          rq[g] = __ldg(reinterpret_cast<const uint4*>(src));
+          rk[g] = __ldg(reinterpret_cast<const uint4*>(src + sw));
+          rv[g] = __ldg(reinterpret_cast<const uint4*>(src + 2 * sw));
+          if (is_img && p.cos_t) {
+            const long long row = p.rope_index ? __ldg(p.rope_index + tok) : tok;
+            const float4* cp = reinterpret_cast<const float4*>(p.cos_t + row * 128 + d0);
+            const float4* sp = reinterpret_cast<const float4*>(p.sin_t + row * 128 + d0);
+            rc[g][0] = __ldg(cp);
+            rc[g][1] = __ldg(cp + 1);
+            rs[g][0] = __ldg(sp);
+            rs[g][1] = __ldg(sp + 1);
+          }
         }
       }
-      const bool rotate = is_img && p.cos_t != nullptr;
-      norm_rope8<kBF16>(q, wq, has_w, p.eps, rotate, rc, rs, half_mask);
-      norm_rope8<kBF16>(k, wk, has_w, p.eps, rotate, rc, rs, half_mask);
-      const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
-      *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
-      *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
-      *reinterpret_cast<uint4*>(p.v + o) = rv;
-      // a CTA of the 4-way split owns exactly one 32-token partial sum; the one-CTA form (kSplit 1,
-      // A/B runs) sums its 128 tokens in one chain, which may differ from the split form in the last
-      // fp32 bit before the 16-bit rounding
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        qsum[i] += q[i];
-        ksum[i] += k[i];
+      for (int g = 0; g < kGroup; ++g) {
+        const long long tok = tok0 + t0 + g;
+        if (t0 + g < n_tok) {   // uniform across the CTA
+          const bool is_img = tok < p.L;
+          float q[8], k[8], wq[8], wk[8];
+          unpack8<kBF16>(rq[g], q);
+          unpack8<kBF16>(rk[g], k);
+          if (has_w) {
+            const float* wqs = s_w[is_img ? 0 : 2] + d0;
+            const float* wks = s_w[is_img ? 1 : 3] + d0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              wq[i] = wqs[i];
+              wk[i] = wks[i];
+            }
+          }
+          const bool rotate = is_img && p.cos_t != nullptr;
+          norm_rope8<kBF16>(q, wq, has_w, p.eps, rotate, rc[g], rs[g], half_mask);
+          norm_rope8<kBF16>(k, wk, has_w, p.eps, rotate, rc[g], rs[g], half_mask);
+          const long long o = ((static_cast<long long>(b) * S + tok) * p.H + h) * 128 + d0;
+          *reinterpret_cast<uint4*>(p.q + o) = pack8<kBF16>(q);
+          *reinterpret_cast<uint4*>(p.k + o) = pack8<kBF16>(k);
+          *reinterpret_cast<uint4*>(p.v + o) = rv[g];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            qsum[i] += q[i];
+            ksum[i] += k[i];
+          }
+        }
       }
     }
     if (p.q_pool) {
