@@ -758,7 +758,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        tf, sample, _, ncores = cpu_sample(wl, "sdpa-port", 16, 6.0)
+        tf, sample, _, ncores = cpu_sample(wl, "sdpa-port", int(os.environ.get("JENGA_REF_NQ", "32")), 3.0)   # same sample as --impl reference
         cpu = {"value": tf, "unit": "TFLOP/s", "cores": ncores, "kind": "sdpa-port",
                "sample": "torch SDPA + expanded block mask (same function as --impl reference): " + sample}
 
