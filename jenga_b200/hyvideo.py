@@ -86,6 +86,20 @@ def attention_prologue(img_qkv: torch.Tensor, txt_qkv: torch.Tensor | None, head
         a.rope_cos, a.rope_sin = cos.data_ptr(), sin.data_ptr()
     else:
         a.rope_cos = a.rope_sin = None
+    if rope_index is not None:
+        # the reference builds hilbert_order from a Python list (CPU int64, sometimes int32): coerce,
+        # and make sure every gathered row exists in the tables
+        if freqs_cis is None:
+            raise ValueError("rope_index given without freqs_cis")
+        rope_index = rope_index.to(device=dev, dtype=torch.int64).contiguous()
+        if rope_index.numel() < L:
+            raise ValueError(f"rope_index has {rope_index.numel()} entries for {L} image tokens")
+        if cos.shape[0] < L and rope_index.numel() > 0:
+            # table shorter than the token count: indices must stay inside it (one host sync, rare path)
+            if int(rope_index[:L].max().item()) >= cos.shape[0] or int(rope_index[:L].min().item()) < 0:
+                raise ValueError("rope_index points outside the cos/sin tables")
+    elif freqs_cis is not None and cos.shape[0] < L:
+        raise ValueError(f"cos/sin tables have {cos.shape[0]} rows for {L} image tokens")
     a.rope_index = rope_index.data_ptr() if rope_index is not None else None
     a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     a.q_pool = qp.data_ptr() if qp is not None else None
