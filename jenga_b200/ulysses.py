@@ -151,6 +151,10 @@ class UlyssesFusedAttention:
     def __init__(self, group=None, variant: str = "hyvideo", groups: int | None = None):
         self.group = group if group is not None else dist.group.WORLD
         self.variant = variant
+        if groups is None:
+            import os
+            env = os.environ.get("JENGA_ULYSSES_GROUPS", "")
+            groups = int(env) if env.isdigit() and int(env) > 0 else None   # tuning / test override
         self.groups = groups
         self._bufs = {}
         self._side = None
