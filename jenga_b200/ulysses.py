@@ -320,8 +320,17 @@ class HostPipelinedUlysses:
         self.s_out = torch.cuda.Stream(self.dev)
         self.ev_in = [torch.cuda.Event() for _ in range(self.G)]
         self.ev_scattered = [None] * self.G
+        self._ev_out = [None, None]     # copy-out completion per result buffer (the result is double-buffered)
+        self._first = True
 
-    def __call__(self, hq, hk, hv, hout, **kw):
+    def finish(self) -> None:
+        """Makes the current stream wait for every copy-out issued so far (call after a run of
+        `__call__(..., wait=False)` steps, before the host reads `hout`)."""
+        torch.cuda.current_stream(self.dev).wait_stream(self.s_out)
+
+    def __call__(self, hq, hk, hv, hout, wait: bool = True, **kw):
+        """wait=False lets consecutive calls overlap: copy-in of step i+1 runs under the attention of
+        step i and the copy-out of step i under step i+1; call finish() before reading `hout`."""
         from .host_pipeline import _copy2d
         n, T, H, D, P, h, G, hg = self.n, self.T, self.H, self.D, self.P, self.h, self.G, self.hg
         for t in (hq, hk, hv, hout):
@@ -330,7 +339,12 @@ class HostPipelinedUlysses:
         es = hq.element_size()
         pitch, width, rows = h * D * es, hg * D * es, (n + T) * P   # rows = (token, destination rank)
         main = torch.cuda.current_stream(self.dev)
-        self.s_in.wait_stream(main)
+        if self._first:
+            self.s_in.wait_stream(main)     # staging buffers were allocated on `main`
+            self._first = False
+        par = self.fused._call & 1          # which of the two result buffers this call fills
+        if self._ev_out[par] is not None:
+            main.wait_event(self._ev_out[par])   # its previous contents have been copied out
         for g in range(G):
             if self.ev_scattered[g] is not None:
                 self.s_in.wait_event(self.ev_scattered[g])   # the previous call has consumed this staging slice
@@ -367,7 +381,11 @@ class HostPipelinedUlysses:
                    joint_tensor_query=self.dq[:, n:] if T else None, joint_tensor_key=self.dk[:, n:] if T else None,
                    joint_tensor_value=self.dv[:, n:] if T else None, joint_strategy="rear" if T else "none",
                    _hooks=dict(pre_scatter=pre_scatter, post_scatter=post_scatter, post_attention=post_attention), **kw)
-        main.wait_stream(self.s_out)
+        ev = torch.cuda.Event()
+        ev.record(self.s_out)
+        self._ev_out[par] = ev
+        if wait:
+            main.wait_stream(self.s_out)
         return hout
 
 
