@@ -368,7 +368,7 @@ def gpu_reference_leg(wl, inp, iters=3):
 # hooks), same weights, same inputs, same GPU.  This is the measured DiT-loop number: one computed
 # denoising step = 20 double + 40 single blocks (jenga_hyvideo.py:132-178); a video = 23 of them.
 # ------------------------------------------------------------------------------------------------
-def dit_forward_leg(wl, inp, n_double, n_single, hidden=3072, heads=24):
+def dit_forward_leg(wl, inp, n_double, n_single, hidden=3072, heads=24, fp8_too=False):
     try:
         from oracle import ref_loader
         if not ref_loader.available():
@@ -454,6 +454,16 @@ def dit_forward_leg(wl, inp, n_double, n_single, hidden=3072, heads=24):
             ref_s, ref_out = timed(lambda: forward(rd, rs, False), 1)
             forward(od, os_, True)
             our_s, our_out = timed(lambda: forward(od, os_, True), 2)
+        fp8_s = None
+        if fp8_too:   # opt-in FP8 P.V variant, reported separately, never the headline
+            from jenga_b200 import attention as _A
+            _A.PV_FP8 = True
+            try:
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    forward(od, os_, True)
+                    fp8_s, fp8_out = timed(lambda: forward(od, os_, True), 2)
+            finally:
+                _A.PV_FP8 = False
         jb.remove_gather_hook()
         rms = ref_out.float().pow(2).mean().sqrt().item()
         diff = (our_out.float() - ref_out.float()).abs()
@@ -467,6 +477,10 @@ def dit_forward_leg(wl, inp, n_double, n_single, hidden=3072, heads=24):
                                            "computed_steps": wl["computed_steps"]},
                 "output_vs_reference": {"max_over_rms": diff.max().item() / rms, "mean_over_rms": diff.mean().item() / rms},
                 "fused_calls": {k_: v_ for k_, v_ in jb.STATS.items()},
+                **({"optin_fp8_pv": {"ours_seconds": fp8_s, "speedup": ref_s / fp8_s,
+                                     "output_vs_reference_mean_over_rms": (fp8_out.float() - ref_out.float()).abs().mean().item() / rms,
+                                     "note": "JENGA_PV_FP8=1: e4m3 P and V in the second product; lower precision, not the headline"}}
+                   if fp8_s else {}),
                 "what": "unmodified reference block classes, random-init bf16 weights; A = reference operator "
                         "(Triton+FA2), B = the same classes through jenga_b200.install hooks"}
     except Exception as e:  # noqa: BLE001
@@ -771,7 +785,7 @@ def main():
     if rank == 0 and world == 1 and args.dit_blocks != "none" and wl["variant"] == "hyvideo" and not args.no_gpu_reference:
         nd, ns = (20, 40) if args.dit_blocks == "full" else (int(v_) for v_ in args.dit_blocks.split(","))
         torch.cuda.empty_cache()
-        ditf = dit_forward_leg(wl, inp, nd, ns)
+        ditf = dit_forward_leg(wl, inp, nd, ns, fp8_too=args.pv_fp8)
         torch.cuda.empty_cache()
 
     fp8v = None

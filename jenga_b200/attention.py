@@ -154,6 +154,12 @@ def quantize_v_fp8(v: torch.Tensor):
     return v8, amax
 
 
+# Opt-in (never the default): route every operator call of this process through the FP8 P.V variant
+# — `jenga_b200.attention.PV_FP8 = True` or JENGA_PV_FP8=1 in the environment.  Lower precision in the
+# second product only (tests/test_fp8_gpu.py has its tolerance row); selection and Q.K^T are unchanged.
+import os as _os
+PV_FP8: bool = _os.environ.get("JENGA_PV_FP8", "0") == "1"
+
 _NBR_CACHE: dict = {}
 # tests set this to a list to record every selection result (bit rows, nb) of calls made deep
 # inside a block forward; None (the default) costs nothing
@@ -315,7 +321,7 @@ def block_sparse_attention_variant(
     limit = S  # no cu_seqlens: seqlens = [context_size] (:336 / wan :452)
     # pv_fp8 (opt-in): V is quantised per head to e4m3 and P.V runs on the FP8 tensor
     # path; NOT the reference's arithmetic — its own tolerance row, never enabled implicitly
-    v8 = quantize_v_fp8(v) if pv_fp8 else None
+    v8 = quantize_v_fp8(v) if (pv_fp8 or PV_FP8) and sp_out is None and q.dtype == torch.bfloat16 else None
     o = _launch(q, k, v, mask_bits, normal_blocks, text_blocks, D ** -0.5, text_amp, normal_blocks,
                 limit, limit, nb * BLOCK, out, seqlen_dev, a_out_dtype, v_fp8=v8)
     if not shape_xfuse:

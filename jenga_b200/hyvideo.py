@@ -130,7 +130,9 @@ def carved_attention_from_pools(q, k, v, pools, *, top_k: int, text_blocks: int 
     elif tuple(out.shape) != (B, S, H, D) or out.dtype != q.dtype or out.stride(3) != 1 or out.stride(2) != D:
         # e.g. the first H*D columns of the single-stream block's concatenation buffer
         raise ValueError("out must be a [B,S,H,D] view with contiguous heads")
-    _launch(q, k, v, bits, n_img, text_blocks, D ** -0.5, text_amp, n_img, S, S, S, out, seq, q.dtype)
+    from . import attention as _A
+    v8 = _A.quantize_v_fp8(v) if (_A.PV_FP8 and q.dtype == torch.bfloat16) else None   # opt-in FP8 P.V variant
+    _launch(q, k, v, bits, n_img, text_blocks, D ** -0.5, text_amp, n_img, S, S, S, out, seq, q.dtype, v_fp8=v8)
     if shape_xfuse:
         return out
     return out.reshape(B, S, H * D) if out.is_contiguous() else out.flatten(2)
