@@ -20,7 +20,7 @@ OUT_DIR = PKG / "_C"
 LIB = OUT_DIR / "libjenga_b200.so"
 STAMP = OUT_DIR / "build.stamp"
 
-CU_SOURCES = ["api.cu", "carved_attn.cu", "carved_attn_v6.cu", "carved_attn_v7.cu", "prologue.cu", "select.cu", "stepcache.cu", "dense_fused.cu", "gilbert_device.cu", "fp8.cu"]
+CU_SOURCES = ["api.cu", "carved_attn.cu", "carved_attn_v6.cu", "carved_attn_v7.cu", "prologue.cu", "prologue_bulk.cu", "select.cu", "stepcache.cu", "dense_fused.cu", "gilbert_device.cu", "fp8.cu"]
 CXX_SOURCES = ["gilbert.cpp"]
 
 NVCC_FLAGS = [

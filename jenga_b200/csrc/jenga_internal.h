@@ -25,6 +25,7 @@ int block_pool_impl(const void* x, void* pooled, void* cast_out, int in_dtype, i
                     long long sh, int n_blocks, cudaStream_t stream);
 int select_blocks_impl(const JengaSelectArgs* a, cudaStream_t stream);
 int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream);
+int hy_prologue_bulk_try(const JengaHyPrologueArgs* a, cudaStream_t stream);  // > 0: not applicable
 int wan_prologue_impl(const JengaWanPrologueArgs* a, cudaStream_t stream);
 
 }  // namespace jenga

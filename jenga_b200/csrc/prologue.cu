@@ -367,6 +367,15 @@ int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream) {
   // shorter last wave saves.  Its pooled means may differ from the default's in the last fp32 bit
   // before the 16-bit rounding (4 x 32-token partial sums instead of one 128-token chain).
   static const int split = [] { const char* e = std::getenv("JENGA_PROLOGUE_SPLIT"); return (e && e[0] == '4') ? 4 : 1; }();
+  // JENGA_PROLOGUE=bulk: the bulk-async (cp.async.bulk) persistent form in prologue_bulk.cu; it returns
+  // a positive value for layouts it does not take (head stride != 128, > 24 heads, misaligned rows,
+  // first use inside a graph capture) and this kernel runs instead.
+  const char* mode = std::getenv("JENGA_PROLOGUE");   // read per call: tests switch it in-process
+  const bool bulk = mode && mode[0] == 'b';
+  if (bulk && split == 1) {
+    const int r = hy_prologue_bulk_try(a, stream);
+    if (r <= 0) return r;
+  }
   const size_t part_bytes = static_cast<size_t>(4) * a->heads * 2 * 128 * sizeof(float);
   if (split == 4 && part_bytes <= 200 * 1024) {
     auto kern = a->dtype == JENGA_BF16 ? hy_prologue_kernel<true, 4> : hy_prologue_kernel<false, 4>;
