@@ -367,12 +367,14 @@ int hy_prologue_impl(const JengaHyPrologueArgs* a, cudaStream_t stream) {
   // shorter last wave saves.  Its pooled means may differ from the default's in the last fp32 bit
   // before the 16-bit rounding (4 x 32-token partial sums instead of one 128-token chain).
   static const int split = [] { const char* e = std::getenv("JENGA_PROLOGUE_SPLIT"); return (e && e[0] == '4') ? 4 : 1; }();
-  // JENGA_PROLOGUE=bulk: the bulk-async (cp.async.bulk) persistent form in prologue_bulk.cu; it returns
-  // a positive value for layouts it does not take (head stride != 128, > 24 heads, misaligned rows,
-  // first use inside a graph capture) and this kernel runs instead.
-  const char* mode = std::getenv("JENGA_PROLOGUE");   // read per call: tests switch it in-process
-  const bool bulk = mode && mode[0] == 'b';
-  if (bulk && split == 1) {
+  // Default: the bulk-async (cp.async.bulk) persistent form in prologue_bulk.cu — 0.75 ms against this
+  // file's 1.12 ms at HY-720p, q/k/v bit-identical (profiles/README.md).  It returns a positive value for
+  // layouts it does not take (head stride != 128, > 24 heads, misaligned rows, first use on a stream
+  // that is being captured into a graph) and then the register-staged kernel below runs instead.
+  // JENGA_PROLOGUE=classic forces the kernel below (read per call: tests switch it in-process).
+  const char* mode = std::getenv("JENGA_PROLOGUE");
+  const bool classic = mode && mode[0] == 'c';
+  if (!classic && split == 1) {
     const int r = hy_prologue_bulk_try(a, stream);
     if (r <= 0) return r;
   }

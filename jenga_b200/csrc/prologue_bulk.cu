@@ -38,11 +38,17 @@ namespace jenga {
 namespace {
 
 constexpr int kBlock = 128;
-constexpr int kStages = 8;
+#ifndef JENGA_PB_STAGES
+#define JENGA_PB_STAGES 10
+#endif
+#ifndef JENGA_PB_STORE_LAG
+#define JENGA_PB_STORE_LAG 3
+#endif
+constexpr int kStages = JENGA_PB_STAGES;
+constexpr int kStoreLag = JENGA_PB_STORE_LAG;   // bulk-store groups whose shared-memory reads may still be pending
 constexpr int kGroupThreads = 384;                 // 24 heads x 16 lanes
 constexpr int kComputeThreads = 2 * kGroupThreads; // even / odd tokens
-constexpr int kThreads = kComputeThreads + 32;     // + one warp: lane 0 producer, lane 16 store thread
-                                                    // (800 threads leave 80 registers each)
+constexpr int kThreads = kComputeThreads + 64;     // + producer warp + store warp (one thread each)
 constexpr int kMaxHeads = 24;
 
 struct BulkParams {
@@ -124,6 +130,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -146,49 +157,73 @@ __device__ __forceinline__ uint32_t mul16x2(uint32_t a, uint32_t b) {
   return r;
 }
 
-// One head row chunk (8 channels in a lane, the row over 16 lanes): norm -> weight -> RoPE, rounding
-// exactly like prologue.cu's norm_rope8; returns the packed 16-bit result and adds it to `sum`.
+// 1/rms of a head row: 8 channels in a lane (4 packed words), the row over 16 lanes.  Same
+// summation order as prologue.cu's norm_rope8 (x0..x7 fma chain, then xor-shuffles 8,4,2,1).
 template <bool kBF16>
-__device__ __forceinline__ uint4 norm_rope_packed(const uint4 raw, const uint4 wpk, const bool has_w, const float eps,
-                                                  const bool rotate, const float (&c)[8], const float (&s)[8],
-                                                  float (&sum)[8]) {
-  const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-  const uint32_t ww[4] = {wpk.x, wpk.y, wpk.z, wpk.w};
-  float x[8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 t = unpack2<kBF16>(rw[j]);
-    x[2 * j] = t.x;
-    x[2 * j + 1] = t.y;
-  }
+__device__ __forceinline__ float row_rnorm(const uint32_t (&w)[4], const float eps) {
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack2<kBF16>(w[j]);
+    ss = fmaf(t.x, t.x, ss);
+    ss = fmaf(t.y, t.y, ss);
+  }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float r = rsqrtf(ss * (1.0f / 128.0f) + eps);
-  uint32_t pk[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    pk[j] = pack2<kBF16>(__fmul_rn(x[2 * j], r), __fmul_rn(x[2 * j + 1], r));
-    if (has_w) pk[j] = mul16x2<kBF16>(pk[j], ww[j]);
+  return rsqrtf(ss * (1.0f / 128.0f) + eps);
+}
+
+// One packed pair (channels 2i, 2i+1): norm -> weight -> RoPE with the rounding points of
+// prologue.cu's norm_rope8; returns the packed result and adds it to the pooling sums.
+template <bool kBF16, bool kW, bool kRot>
+__device__ __forceinline__ uint32_t finish_pair(const uint32_t raw, const float inv, const uint32_t w, const float c0,
+                                                const float c1, const float s0, const float s1, float& sum0, float& sum1) {
+  const float2 x = unpack2<kBF16>(raw);
+  uint32_t pk = pack2<kBF16>(__fmul_rn(x.x, inv), __fmul_rn(x.y, inv));
+  if constexpr (kW) pk = mul16x2<kBF16>(pk, w);
+  float2 y = unpack2<kBF16>(pk);
+  if constexpr (kRot) {
+    const float a0 = __fadd_rn(__fmul_rn(y.x, c0), __fmul_rn(-y.y, s0));
+    const float a1 = __fadd_rn(__fmul_rn(y.y, c1), __fmul_rn(y.x, s1));
+    pk = pack2<kBF16>(a0, a1);
+    y = unpack2<kBF16>(pk);
   }
-  if (rotate) {
+  sum0 += y.x;
+  sum1 += y.y;
+  return pk;
+}
+
+// A token's q and k rows of one lane (8 channels each), in place in the ring stage.  Two halves of the
+// 8 channels: each half's cos/sin chunk and weight pair is loaded once and serves q and k.
+template <bool kBF16, bool kW, bool kRot>
+__device__ __forceinline__ void token_rows(const uint32_t q_addr, const uint32_t k_addr, const uint32_t cs_addr,
+                                           const uint32_t w_addr, const float eps, const bool active, float (&qsum)[8],
+                                           float (&ksum)[8]) {
+  const uint4 q4 = lds128(q_addr);
+  const uint4 k4 = lds128(k_addr);
+  uint32_t rq[4] = {q4.x, q4.y, q4.z, q4.w}, rk[4] = {k4.x, k4.y, k4.z, k4.w};
+  const float inv_q = row_rnorm<kBF16>(rq, eps), inv_k = row_rnorm<kBF16>(rk, eps);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 y = unpack2<kBF16>(pk[j]);
-      const float a0 = __fadd_rn(__fmul_rn(y.x, c[2 * j]), __fmul_rn(-y.y, s[2 * j]));
-      const float a1 = __fadd_rn(__fmul_rn(y.y, c[2 * j + 1]), __fmul_rn(y.x, s[2 * j + 1]));
-      pk[j] = pack2<kBF16>(a0, a1);
+  for (int half = 0; half < 2; ++half) {
+    float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = c4;
+    if constexpr (kRot) {
+      c4 = lds128f(cs_addr + 16u * half);
+      s4 = lds128f(cs_addr + 512u + 16u * half);
     }
+    uint2 wq = make_uint2(0u, 0u), wk = wq;
+    if constexpr (kW) {
+      wq = lds64(w_addr + 8u * half);
+      wk = lds64(w_addr + 256u + 8u * half);
+    }
+    rq[2 * half] = finish_pair<kBF16, kW, kRot>(rq[2 * half], inv_q, wq.x, c4.x, c4.y, s4.x, s4.y, qsum[4 * half], qsum[4 * half + 1]);
+    rq[2 * half + 1] = finish_pair<kBF16, kW, kRot>(rq[2 * half + 1], inv_q, wq.y, c4.z, c4.w, s4.z, s4.w, qsum[4 * half + 2], qsum[4 * half + 3]);
+    rk[2 * half] = finish_pair<kBF16, kW, kRot>(rk[2 * half], inv_k, wk.x, c4.x, c4.y, s4.x, s4.y, ksum[4 * half], ksum[4 * half + 1]);
+    rk[2 * half + 1] = finish_pair<kBF16, kW, kRot>(rk[2 * half + 1], inv_k, wk.y, c4.z, c4.w, s4.z, s4.w, ksum[4 * half + 2], ksum[4 * half + 3]);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 y = unpack2<kBF16>(pk[j]);
-    sum[2 * j] += y.x;
-    sum[2 * j + 1] += y.y;
+  if (active) {
+    sts128(q_addr, make_uint4(rq[0], rq[1], rq[2], rq[3]));
+    sts128(k_addr, make_uint4(rk[0], rk[1], rk[2], rk[3]));
   }
-  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 template <bool kBF16>
@@ -237,9 +272,9 @@ hy_prologue_bulk_kernel(const BulkParams p) {
   }
   __syncthreads();
 
-  if (warp == kComputeThreads / 32) {
+  if (warp >= kComputeThreads / 32) {
     const int lane = tid & 31;
-    if (lane == 0) {
+    if (warp == kComputeThreads / 32 && lane == 0) {
       // ---------------------------------------------------------------- producer (one thread)
       uint32_t n = 0;
       Item it;
@@ -263,7 +298,7 @@ hy_prologue_bulk_kernel(const BulkParams p) {
             const int t = t0 + j;
             if (t < it.nt) {
               const uint32_t s = n % kStages;
-              if (n >= kStages) mbar_wait_relaxed(&bar_empty[s], ((n / kStages) - 1) & 1, nullptr);
+              if (n >= kStages) mbar_wait(&bar_empty[s], ((n / kStages) - 1) & 1, nullptr);
               const long long tok = it.tok0 + t;
               const bool is_img = tok < p.L;
               const bool rotate = is_img && p.cos_t != nullptr;
@@ -286,26 +321,28 @@ hy_prologue_bulk_kernel(const BulkParams p) {
           for (int j = 0; j < kAhead; ++j) cur[j] = nxt[j];
         }
       }
-    } else if (lane == 16) {
+    } else if (warp == kComputeThreads / 32 + 1 && lane == 0) {
       // ---------------------------------------------------------------- store thread
       uint32_t n = 0;
       Item it;
       for (int i = 0; get_item(p, i, it); ++i) {
         for (int t = 0; t < it.nt; ++t, ++n) {
           const uint32_t s = n % kStages;
-          mbar_wait_relaxed(&bar_done[s], (n / kStages) & 1, nullptr);
+          mbar_wait(&bar_done[s], (n / kStages) & 1, nullptr);
           const long long o = ((static_cast<long long>(it.b) * S + it.tok0 + t) * p.H) * 128;
           const uint32_t src = stage0 + s * stage_bytes;
           bulk_store(p.q + o, src, row_bytes);
           bulk_store(p.k + o, src + row_bytes, row_bytes);
           bulk_store(p.v + o, src + 2u * row_bytes, row_bytes);
           bulk_commit();
-          if (n >= 1) {
-            bulk_wait_read<1>();   // the previous token's stores have read their stage
-            mbar_arrive(&bar_empty[(n - 1) % kStages]);
+          if (n >= kStoreLag) {
+            bulk_wait_read<kStoreLag>();   // the stores of token n - kStoreLag have read their stage
+            mbar_arrive(&bar_empty[(n - kStoreLag) % kStages]);
           }
         }
       }
+      // tokens n - kStoreLag .. n - 1 still own their stages; nobody waits for those, but the stores
+      // must have left shared memory before the CTA exits
       bulk_wait_all();
     }
   } else {
@@ -319,43 +356,42 @@ hy_prologue_bulk_kernel(const BulkParams p) {
     const int d0 = lane16 * 8;
     const uint32_t my_off = static_cast<uint32_t>(h) * 256u + static_cast<uint32_t>(lane16) * 16u;
     const uint32_t w_base = smem_u32(s_w) + static_cast<uint32_t>(lane16) * 16u;
-    uint32_t n = 0;
+    static_assert(kStages % 2 == 0, "a group's tokens advance two ring stages at a time");
+    uint32_t s = static_cast<uint32_t>(g), ph = 0;   // ring stage and phase of this group's next token
+    uint32_t nbase = 0;                              // tokens of the items before this one
+    const uint32_t bar_full0 = smem_u32(bar_full), bar_done0 = smem_u32(bar_done);
+    const uint32_t cs_off = 3u * row_bytes + static_cast<uint32_t>(lane16) * 32u;
     Item it;
     for (int i = 0; get_item(p, i, it); ++i) {
       float qsum[8], ksum[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) qsum[e] = ksum[e] = 0.f;
-      for (int t = 0; t < it.nt; ++t, ++n) {
-        if ((n & 1u) != static_cast<uint32_t>(g)) continue;
-        const uint32_t s = n % kStages;
-        mbar_wait(&bar_full[s], (n / kStages) & 1, nullptr);
-        const long long tok = it.tok0 + t;
-        const bool is_img = tok < p.L;
+      const long long img_left = p.L - it.tok0;
+      const int n_img = img_left <= 0 ? 0 : (img_left < it.nt ? static_cast<int>(img_left) : it.nt);
+      for (int t = static_cast<int>((static_cast<uint32_t>(g) - nbase) & 1u); t < it.nt; t += 2) {
+        mbar_wait(reinterpret_cast<uint64_t*>(__cvta_shared_to_generic(bar_full0 + 8u * s)), ph, nullptr);
+        const bool is_img = t < n_img;
         const bool rotate = is_img && p.cos_t != nullptr;
         const uint32_t st = stage0 + s * stage_bytes;
-        // q then k, each with its own loads of the raw row, the weights and the cos/sin chunk: the
-        // second set of LDS is cheaper than keeping 28 more values live (72 registers per thread)
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          const uint32_t row = st + (which ? row_bytes : 0u) + my_off;
-          const uint4 raw = lds128(row);
-          float c[8], sn[8];
-          if (rotate) {
-            const uint32_t cs = st + 3u * row_bytes + static_cast<uint32_t>(d0) * 4u;
-            const float4 c0 = lds128f(cs), c1 = lds128f(cs + 16u), s0 = lds128f(cs + 512u), s1 = lds128f(cs + 528u);
-            c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-            sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
-          }
-          uint4 wpk = make_uint4(0, 0, 0, 0);
-          if (has_w) wpk = lds128(w_base + (is_img ? 0u : 512u) + (which ? 256u : 0u));
-          const uint4 o = which ? norm_rope_packed<kBF16>(raw, wpk, has_w, p.eps, rotate, c, sn, ksum)
-                                : norm_rope_packed<kBF16>(raw, wpk, has_w, p.eps, rotate, c, sn, qsum);
-          if (active) sts128(row, o);
+        const uint32_t qa = st + my_off, ka = qa + row_bytes, ca = st + cs_off;
+        const uint32_t wa = w_base + (is_img ? 0u : 512u);   // this token's packed norm weights (q; k at +256)
+        if (has_w) {
+          if (rotate) token_rows<kBF16, true, true>(qa, ka, ca, wa, p.eps, active, qsum, ksum);
+          else token_rows<kBF16, true, false>(qa, ka, ca, wa, p.eps, active, qsum, ksum);
+        } else {
+          if (rotate) token_rows<kBF16, false, true>(qa, ka, ca, wa, p.eps, active, qsum, ksum);
+          else token_rows<kBF16, false, false>(qa, ka, ca, wa, p.eps, active, qsum, ksum);
         }
         fence_proxy_async_smem();   // the bulk store reads these rows through the async proxy
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&bar_done[s]);
+        if ((tid & 31) == 0) mbar_arrive(reinterpret_cast<uint64_t*>(__cvta_shared_to_generic(bar_done0 + 8u * s)));
+        s += 2;
+        if (s >= kStages) {
+          s -= kStages;
+          ph ^= 1u;
+        }
       }
+      nbase += static_cast<uint32_t>(it.nt);
       if (p.q_pool) {
         // group 1 (odd tokens) hands its sums to group 0 through shared memory
         float* mine = s_pool + (h * 2) * 128 + d0;

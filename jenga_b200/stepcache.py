@@ -223,7 +223,9 @@ class GraphedHotPath:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the stream the warm-up ran on: per-stream state created there (the bulk prologue's
+        # scratch for split blocks, csrc/prologue_bulk.cu) exists, so the capture takes the same kernels
+        with torch.cuda.graph(self.graph, stream=side):
             self.outputs = fn(*static_inputs)
 
     def copy_inputs(self, *new_inputs) -> None:

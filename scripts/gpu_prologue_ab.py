@@ -1,5 +1,5 @@
 """A/B of the two forms of the HunyuanVideo prologue at HY-720p (classic register-staged kernel vs the
-bulk-async persistent kernel, JENGA_PROLOGUE=bulk): CUDA-event time, GB/s against MEASURED_PEAKS.json."""
+bulk-async persistent kernel, the default; JENGA_PROLOGUE=classic selects the other): CUDA-event time, GB/s against MEASURED_PEAKS.json."""
 import json, os, sys, torch
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -29,10 +29,7 @@ def timeit(fn, n=20):
 for label, idx in (("identity rope rows", None), ("rope_index = random permutation", index)):
     outs = {}
     for mode in ("classic", "bulk"):
-        if mode == "bulk":
-            os.environ["JENGA_PROLOGUE"] = "bulk"
-        else:
-            os.environ.pop("JENGA_PROLOGUE", None)
+        os.environ["JENGA_PROLOGUE"] = mode
         fn = lambda: attention_prologue(img, txt, H, *ws, eps=1e-6, freqs_cis=(cos, sin), rope_index=idx)
         ms = timeit(fn)
         outs[mode] = fn()

@@ -1,5 +1,5 @@
-"""GPU parity of the bulk-async form of the HunyuanVideo prologue (csrc/prologue_bulk.cu) against the
-classic kernel: q, k, v bit-identical (same rounding chain), pooled means within the summation-order
+"""GPU parity of the bulk-async form of the HunyuanVideo prologue (csrc/prologue_bulk.cu, the default) against
+the register-staged kernel (JENGA_PROLOGUE=classic): q, k, v bit-identical (same rounding chain), pooled means within the summation-order
 tolerance of tests/test_prologue_gpu.py.  Grid sizes are forced with JENGA_PROLOGUE_CTAS so that small
 inputs go through whole-block chunks, split left-over blocks and the ticket combine."""
 import os
@@ -67,7 +67,7 @@ def test_bulk_prologue_equals_classic(B, L, T, H, dt, has_w, rope, use_index, ct
     def call():
         return attention_prologue(img, txt, H, *ws, 1e-6, fc, rope_index=index)
 
-    q0, k0, v0, (qp0, kp0) = _run(None, 0, call)
+    q0, k0, v0, (qp0, kp0) = _run("classic", 0, call)
     q1, k1, v1, (qp1, kp1) = _run("bulk", ctas, call)
     for a, b, name in ((q0, q1, "q"), (k0, k1, "k"), (v0, v1, "v")):
         assert torch.equal(a.view(torch.int16), b.view(torch.int16)), name
@@ -89,14 +89,14 @@ def test_bulk_prologue_declines_unsupported_layouts():
     dev = "cuda"
     H = 26
     img = torch.randn((1, 256, 3 * H * 128), device=dev).bfloat16()
-    q0, k0, v0, _ = _run(None, 0, lambda: attention_prologue(img, None, H))
+    q0, k0, v0, _ = _run("classic", 0, lambda: attention_prologue(img, None, H))
     q1, k1, v1, _ = _run("bulk", 0, lambda: attention_prologue(img, None, H))
     assert torch.equal(q0.view(torch.int16), q1.view(torch.int16))
     assert torch.equal(v0.view(torch.int16), v1.view(torch.int16))
     H = 24
     wide = torch.randn((1, 300, 3 * H * 128 + 512), device=dev).bfloat16()
     view = wide[:, :, :3 * H * 128]
-    q0, k0, v0, (p0, _) = _run(None, 0, lambda: attention_prologue(view, None, H))
+    q0, k0, v0, (p0, _) = _run("classic", 0, lambda: attention_prologue(view, None, H))
     q1, k1, v1, (p1, _) = _run("bulk", 3, lambda: attention_prologue(view, None, H))
     assert torch.equal(q0.view(torch.int16), q1.view(torch.int16)) and torch.equal(k0.view(torch.int16), k1.view(torch.int16))
     assert torch.equal(v0.view(torch.int16), v1.view(torch.int16))
