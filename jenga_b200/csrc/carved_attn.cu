@@ -42,6 +42,13 @@
 #define JENGA_QK_FULL 0
 #endif
 
+// L2 residency hints (experiment, profiles/README.md): 1 = Q loads evict_first, K/V loads evict_last,
+// O stores streaming.  K+V of a head (59 MB at HY-720p) are re-read by every q block of the head; Q and O
+// are touched once.
+#ifndef JENGA_ATTN_L2HINT
+#define JENGA_ATTN_L2HINT 0
+#endif
+
 namespace jenga {
 
 namespace {
@@ -170,8 +177,16 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
     // =============================== TMA producer ===============================
     if (n_tiles > 0 && elect_one()) {
       mbar_arrive_expect_tx(&bars[Q_FULL], kQTileBytes);
+#if JENGA_ATTN_L2HINT
+      const uint64_t pol_q = l2_policy_evict_first(), pol_kv = l2_policy_evict_last();
+      tma_load_4d_hint(sQ, &tm_q, &bars[Q_FULL], 0, static_cast<int>(q_row0), h, b, pol_q);
+      tma_load_4d_hint(sQ + kQHalfBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b, pol_q);
+#define JENGA_KV_LOAD(dst, map, bar, c0, c1, c2, c3) tma_load_4d_hint(dst, map, bar, c0, c1, c2, c3, pol_kv)
+#else
       tma_load_4d(sQ, &tm_q, &bars[Q_FULL], 0, static_cast<int>(q_row0), h, b);
       tma_load_4d(sQ + kQHalfBytes, &tm_q, &bars[Q_FULL], 64, static_cast<int>(q_row0), h, b);
+#define JENGA_KV_LOAD(dst, map, bar, c0, c1, c2, c3) tma_load_4d(dst, map, bar, c0, c1, c2, c3)
+#endif
       // Loads are issued in the order the tensor pipe consumes them,
       //   K_a(0) K_b(0) | V_a(0) K_a(1) | V_b(0) K_b(1) | V_a(1) K_a(2) | ...
       // so a wait for a V slot never holds up the K half the next QK needs first (A/B on one
@@ -183,8 +198,8 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
         uint8_t* dst = sK + hh * kKVBoxBytes;
         JENGA_PRODUCER_WAIT(&bars[K_EMPTY0 + hh], par, p.err_flag);
         mbar_arrive_expect_tx(&bars[K_FULL0 + hh], kKVSlotBytes);
-        tma_load_4d(dst, &tm_k, &bars[K_FULL0 + hh], 0, row0, h, b);
-        tma_load_4d(dst + 2 * kKVBoxBytes, &tm_k, &bars[K_FULL0 + hh], 64, row0, h, b);
+        JENGA_KV_LOAD(dst, &tm_k, &bars[K_FULL0 + hh], 0, row0, h, b);
+        JENGA_KV_LOAD(dst + 2 * kKVBoxBytes, &tm_k, &bars[K_FULL0 + hh], 64, row0, h, b);
       };
       auto load_v = [&](int blk, int hh, uint32_t par) {
         const int row0 = blk * kBlock + hh * kHalf;
@@ -192,11 +207,11 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
         JENGA_PRODUCER_WAIT(&bars[V_EMPTY0 + hh], par, p.err_flag);
         if constexpr (kPvFp8) {   // 64 keys x 128 one-byte channels = one 8 KB box
           mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVBoxBytes);
-          tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
+          JENGA_KV_LOAD(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
         } else {
           mbar_arrive_expect_tx(&bars[V_FULL0 + hh], kKVSlotBytes);
-          tma_load_4d(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
-          tma_load_4d(dst + kKVBoxBytes, &tm_v, &bars[V_FULL0 + hh], 64, row0, h, b);
+          JENGA_KV_LOAD(dst, &tm_v, &bars[V_FULL0 + hh], 0, row0, h, b);
+          JENGA_KV_LOAD(dst + kKVBoxBytes, &tm_v, &bars[V_FULL0 + hh], 64, row0, h, b);
         }
       };
       BlockWalker it(s_mask, nwords);
@@ -525,7 +540,11 @@ carved_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q,
             for (int r = 0; r < n_dst; ++r)
               *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.peer_out[r]) + o_off + cc + i) = v;
           } else if (!p.out_f32) {
+#if JENGA_ATTN_L2HINT
+            __stcs(reinterpret_cast<uint4*>(obase + o_off + cc + i), v);
+#else
             *reinterpret_cast<uint4*>(obase + o_off + cc + i) = v;
+#endif
           } else {  // wan/…:530-532: the 16-bit result is widened back to the query dtype
             float* orow32 = reinterpret_cast<float*>(p.out) + o_off;
             float2 t0 = unpack2<kBF16>(e[0]), t1 = unpack2<kBF16>(e[1]);
