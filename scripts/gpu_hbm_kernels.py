@@ -69,3 +69,22 @@ t0 = time.perf_counter(); gilbert.mapping_tensors(32, 45, 80); gilbert.block_nei
 print(f"host walker tables + adjacency: {(t1 - t0) * 1e3:.1f} ms")
 for k_, (ms, b) in res2.items():
     print(f"{k_:26s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}" if b else f"{k_:26s} {ms:8.3f} ms")
+
+# ---- Wan-14B shapes: the WanRMSNorm + fp64-RoPE prologue and the fp32 -> bf16 cast fused with the block pooling
+from jenga_b200 import wan as WAN
+Lw, Hw = 75600, 40
+xw = torch.randn(1, Lw, Hw * 128, device=dev)
+ww = torch.ones(Hw * 128, device=dev)
+freqs = WAN.rope_freqs(128)
+_, h2lw = gilbert.mapping_tensors(21, 45, 80, sliced=True)
+h2lw = h2lw.to(dev)
+res3 = {}
+ms = timeit(lambda: WAN.norm_rope(xw, ww, Hw, (21, 45, 80), freqs, h2lw)); res3["wan_prologue (f32 in)"] = (ms, Lw * Hw * 128 * (4 + 2))
+xb = xw.bfloat16(); wb = ww.bfloat16()
+ms = timeit(lambda: WAN.norm_rope(xb, wb, Hw, (21, 45, 80), freqs, h2lw)); res3["wan_prologue (bf16 in)"] = (ms, Lw * Hw * 128 * (2 + 2))
+q32 = torch.randn(1, Lw, Hw, 128, device=dev)
+castbuf = torch.empty(q32.shape, dtype=torch.bfloat16, device=dev)
+nbw = (Lw + 127) // 128
+ms = timeit(lambda: block_pool(q32, nbw, cast_out=castbuf)); res3["block_pool f32->bf16 + cast"] = (ms, Lw * Hw * 128 * (4 + 2))
+for k_, (ms, b) in res3.items():
+    print(f"{k_:30s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}")

@@ -101,3 +101,35 @@ def test_bulk_prologue_declines_unsupported_layouts():
     assert torch.equal(q0.view(torch.int16), q1.view(torch.int16)) and torch.equal(k0.view(torch.int16), k1.view(torch.int16))
     assert torch.equal(v0.view(torch.int16), v1.view(torch.int16))
     assert (p0.float() - p1.float()).abs().max() <= 2.0 ** -8 * p0.float().abs().max() + 1e-6
+
+
+@pytest.mark.parametrize("dt,heads,grid", [(torch.float32, 12, (3, 6, 8)), (torch.bfloat16, 12, (3, 6, 8)),
+                                           (torch.float32, 40, (2, 5, 7)), (torch.bfloat16, 5, (4, 4, 4))])
+def test_wan_prologue_vector_form_equals_scalar_form(dt, heads, grid):
+    """The 128-threads-per-token vector kernel against the one-warp-per-token kernel it replaced: same arithmetic
+    per element, only the fp32 summation order of mean(x^2) differs -> <= 1 bf16 ulp, >= 99.8 % bit-identical."""
+    from jenga_b200 import wan
+    dev = "cuda"
+    L = grid[0] * grid[1] * grid[2] + 37          # some tokens beyond the grid get no rotation
+    g = torch.Generator().manual_seed(99 + heads)
+    x = (torch.randn((2, L, heads * 128), generator=g) * 1.3).to(dt).to(dev)
+    w = (1 + 0.2 * torch.randn(heads * 128, generator=g)).to(dt).to(dev)
+    remap = torch.randperm(grid[0] * grid[1] * grid[2], generator=g).to(dev)
+    freqs = wan.rope_freqs(128)
+    outs = {}
+    for mode in ("scalar", "vector"):
+        old = os.environ.get("JENGA_WAN_PROLOGUE")
+        os.environ["JENGA_WAN_PROLOGUE"] = mode
+        try:
+            outs[mode] = wan.norm_rope(x, w, heads, grid, freqs, remap, eps=1e-6)
+            torch.cuda.synchronize()
+        finally:
+            if old is None:
+                os.environ.pop("JENGA_WAN_PROLOGUE", None)
+            else:
+                os.environ["JENGA_WAN_PROLOGUE"] = old
+    a, b = outs["scalar"].float(), outs["vector"].float()
+    ulp = torch.exp2(torch.floor(torch.log2(a.abs().clamp_min(1e-30))) - 7)
+    assert ((a - b).abs() / ulp).max() <= 1.0
+    same = (outs["scalar"].view(torch.int16) == outs["vector"].view(torch.int16)).float().mean().item()
+    assert same >= 0.998, same
