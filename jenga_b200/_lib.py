@@ -92,7 +92,7 @@ class JengaWanPrologueArgs(C.Structure):
         ("stride_b", C.c_int64), ("stride_s", C.c_int64), ("eps", C.c_float),
         ("freqs", C.c_void_p), ("freq_rows", C.c_int32),
         ("grid_f", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32),
-        ("freq_remap", C.c_void_p), ("out", C.c_void_p),
+        ("freq_remap", C.c_void_p), ("out", C.c_void_p), ("freqs_hilo", C.c_void_p),
     ]
 
 

@@ -20,6 +20,7 @@
 // (8 channels per lane), so the norm reduction is 4 shuffles and each lane keeps the pooling
 // partial sums of its own 8 channels across the 128 tokens of the block.
 #include <cstdlib>
+#include <cstring>
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -430,7 +431,20 @@ struct WanPrologueParams {
   int gf, gh, gw;       // latent grid (F, H, W); tokens >= F*H*W get no rotation (:66)
   const long long* remap;  // optional [F*H*W]: position of token i (hilbert_order)
   uint16_t* out;        // [B, L, H, 128] bf16, contiguous
+  const float* hilo;    // optional [rows, 64, 4] fp32 split of freqs (vector kernel, FP32-pipe rotation)
 };
+
+// a*fa - b*fb with fa = fah + fal, fb = fbh + fbl: products split exactly with an FMA, the difference
+// of the leading terms with a two-sum, everything small added in plain fp32 (relative error ~2^-45)
+__device__ __forceinline__ float comp_diff(float a, float fah, float fal, float b, float fbh, float fbl) {
+  const float p1 = __fmul_rn(a, fah), e1 = __fmaf_rn(a, fah, -p1);
+  const float p2 = __fmul_rn(b, fbh), e2 = __fmaf_rn(b, fbh, -p2);
+  const float s = __fsub_rn(p1, p2);
+  const float bb = __fsub_rn(s, p1);
+  const float err = __fadd_rn(__fsub_rn(p1, __fsub_rn(s, bb)), __fsub_rn(-p2, bb));
+  const float small = __fadd_rn(__fadd_rn(__fsub_rn(e1, e2), err), __fsub_rn(__fmul_rn(a, fal), __fmul_rn(b, fbl)));
+  return __fadd_rn(s, small);
+}
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
@@ -592,10 +606,16 @@ wan_prologue_vec_kernel(const WanPrologueParams p) {
         if (rotate) {
           const int jj = ((c0 + 2 * i) & 127) >> 1;          // complex index inside the head
           const int row = jj < s0 ? fi : (jj < s0 + c3 ? hi_ : wi);
-          const double2 fr = __ldg(reinterpret_cast<const double2*>(p.freqs) + static_cast<long long>(row) * 64 + jj);
-          const double a = static_cast<double>(y[0]), bb = static_cast<double>(y[1]);
-          o0 = static_cast<float>(a * fr.x - bb * fr.y);      // complex128 product, then .float()
-          o1 = static_cast<float>(a * fr.y + bb * fr.x);
+          if (p.hilo) {   // (re_hi, im_hi, re_lo, im_lo): the complex128 product rounded to fp32, on the FP32 pipe
+            const float4 fr = __ldg(reinterpret_cast<const float4*>(p.hilo) + static_cast<long long>(row) * 64 + jj);
+            o0 = comp_diff(y[0], fr.x, fr.z, y[1], fr.y, fr.w);          // a*re - b*im
+            o1 = comp_diff(y[0], fr.y, fr.w, -y[1], fr.x, fr.z);         // a*im + b*re
+          } else {
+            const double2 fr = __ldg(reinterpret_cast<const double2*>(p.freqs) + static_cast<long long>(row) * 64 + jj);
+            const double a = static_cast<double>(y[0]), bb = static_cast<double>(y[1]);
+            o0 = static_cast<float>(a * fr.x - bb * fr.y);      // complex128 product, then .float()
+            o1 = static_cast<float>(a * fr.y + bb * fr.x);
+          }
         }
         packed[i] = pack2<true>(o0, o1);
       }
@@ -626,13 +646,20 @@ int wan_prologue_impl(const JengaWanPrologueArgs* a, cudaStream_t stream) {
   p.gf = a->grid_f; p.gh = a->grid_h; p.gw = a->grid_w;
   p.remap = reinterpret_cast<const long long*>(a->freq_remap);
   p.out = static_cast<uint16_t*>(a->out);
-  // vector form when rows are 16-byte addressable; JENGA_WAN_PROLOGUE=scalar forces the one-warp-per-token kernel
+  p.hilo = a->freqs ? a->freqs_hilo : nullptr;
+  // Vector form when the caller supplied the fp32 split of the table (the fp64 pipe, not memory, bounds the
+  // rotation: scalar kernel 0.64-0.71 ms at Wan-14B size, vector kernel WITH fp64 1.0 ms) and rows are 16-byte
+  // addressable; JENGA_WAN_PROLOGUE=scalar forces the one-warp-per-token fp64 kernel, =vector64 the vector
+  // kernel with the fp64 rotation.
   const int esz = p.x_f32 ? 4 : 2, wsz = p.w_f32 ? 4 : 2;
   const char* wmode = std::getenv("JENGA_WAN_PROLOGUE");
-  const bool vec_ok = !(wmode && wmode[0] == 's') && p.C % 8 == 0 && p.C / 8 <= 6 * kWanThreads &&
+  const bool want64 = wmode && wmode[0] == 'v' && wmode[1] == 'e' && std::strlen(wmode) >= 8;   // "vector64"
+  if (want64) p.hilo = nullptr;
+  const bool vec_ok = !(wmode && wmode[0] == 's') && (p.hilo || !p.freqs || want64) && p.C % 8 == 0 && p.C / 8 <= 6 * kWanThreads &&
                       reinterpret_cast<uintptr_t>(p.x) % 16 == 0 && (p.sb * esz) % 16 == 0 && (p.ss * esz) % 16 == 0 &&
                       (!p.w || reinterpret_cast<uintptr_t>(p.w) % 16 == 0) && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
-                      (!p.freqs || reinterpret_cast<uintptr_t>(p.freqs) % 16 == 0);
+                      (!p.freqs || reinterpret_cast<uintptr_t>(p.freqs) % 16 == 0) &&
+                      (!p.hilo || reinterpret_cast<uintptr_t>(p.hilo) % 16 == 0);
   (void)wsz;
   if (vec_ok) {
     long long pairs = (a->tokens + 1) / 2;

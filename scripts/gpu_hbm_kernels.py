@@ -79,12 +79,16 @@ freqs = WAN.rope_freqs(128)
 _, h2lw = gilbert.mapping_tensors(21, 45, 80, sliced=True)
 h2lw = h2lw.to(dev)
 res3 = {}
-ms = timeit(lambda: WAN.norm_rope(xw, ww, Hw, (21, 45, 80), freqs, h2lw)); res3["wan_prologue (f32 in)"] = (ms, Lw * Hw * 128 * (4 + 2))
+import os
 xb = xw.bfloat16(); wb = ww.bfloat16()
-ms = timeit(lambda: WAN.norm_rope(xb, wb, Hw, (21, 45, 80), freqs, h2lw)); res3["wan_prologue (bf16 in)"] = (ms, Lw * Hw * 128 * (2 + 2))
+for mode in ("vector", "vector64", "scalar"):
+    os.environ["JENGA_WAN_PROLOGUE"] = mode
+    ms = timeit(lambda: WAN.norm_rope(xw, ww, Hw, (21, 45, 80), freqs, h2lw)); res3[f"wan_prologue {mode} (f32 in)"] = (ms, Lw * Hw * 128 * (4 + 2))
+    ms = timeit(lambda: WAN.norm_rope(xb, wb, Hw, (21, 45, 80), freqs, h2lw)); res3[f"wan_prologue {mode} (bf16 in)"] = (ms, Lw * Hw * 128 * (2 + 2))
+os.environ.pop("JENGA_WAN_PROLOGUE", None)
 q32 = torch.randn(1, Lw, Hw, 128, device=dev)
 castbuf = torch.empty(q32.shape, dtype=torch.bfloat16, device=dev)
 nbw = (Lw + 127) // 128
 ms = timeit(lambda: block_pool(q32, nbw, cast_out=castbuf)); res3["block_pool f32->bf16 + cast"] = (ms, Lw * Hw * 128 * (4 + 2))
 for k_, (ms, b) in res3.items():
-    print(f"{k_:30s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}")
+    print(f"{k_:34s} {ms:8.3f} ms  {b/ms/1e6:9.1f} GB/s  frac_of_hbm_peak {b/ms/1e6/peak:5.2f}")
