@@ -513,11 +513,10 @@ wan_prologue_kernel(const WanPrologueParams p) {
 }
 
 
-// Vector form (C % 8 == 0, 16-byte aligned rows): 128 threads per token, the token's channels stay in
-// registers (kVec 8-channel vectors per thread), one block reduction for mean(x^2), 16-byte loads and
-// stores.  Same arithmetic per element as wan_prologue_kernel above (which remains the fallback for odd
-// layouts); only the fp32 summation order of mean(x^2) differs.  The scalar form issued ~560 2- and
-// 4-byte loads per lane and token and ran at 0.34-0.46 of the HBM peak at Wan-14B size.
+// Experimental vector form (JENGA_WAN_PROLOGUE=vector|vector64; C % 8 == 0, 16-byte aligned rows): 128 threads
+// per token, the token's channels stay in registers (kVec 8-channel vectors per thread), one block reduction for
+// mean(x^2), 16-byte loads and stores.  Same arithmetic per element as wan_prologue_kernel above (the default);
+// only the fp32 summation order of mean(x^2) differs.  Measured slower than the default (see the launcher).
 constexpr int kWanThreads = 128;
 
 template <int kVec>
@@ -566,19 +565,30 @@ wan_prologue_vec_kernel(const WanPrologueParams p) {
     const float r = rsqrtf((rr[0] + rr[1] + rr[2] + rr[3]) / static_cast<float>(p.C) + p.eps);
     if (!live) continue;
     const bool rotate = tok < n_grid && p.freqs != nullptr;
-    int fi = 0, hi_ = 0, wi = 0;
+    // The rotation of a channel depends on its position inside the head only, and a thread's vectors
+    // t, t+128, ... all sit at the same position ((8t) mod 128): four complex factors per token serve
+    // every vector of the thread.
+    float4 fr32[4];
+    double2 fr64[4];
     if (rotate) {
       const long long pos = p.remap ? __ldg(p.remap + tok) : tok;
-      fi = static_cast<int>(pos / (static_cast<long long>(p.gh) * p.gw));
+      const int fi = static_cast<int>(pos / (static_cast<long long>(p.gh) * p.gw));
       const int rem = static_cast<int>(pos - static_cast<long long>(fi) * p.gh * p.gw);
-      hi_ = rem / p.gw;
-      wi = rem - hi_ * p.gw;
+      const int hi_ = rem / p.gw;
+      const int wi = rem - hi_ * p.gw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int jj = (t & 15) * 4 + i;                     // complex index inside the head
+        const int row = jj < s0 ? fi : (jj < s0 + c3 ? hi_ : wi);
+        const long long idx = static_cast<long long>(row) * 64 + jj;
+        if (p.hilo) fr32[i] = __ldg(reinterpret_cast<const float4*>(p.hilo) + idx);
+        else fr64[i] = __ldg(reinterpret_cast<const double2*>(p.freqs) + idx);
+      }
     }
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
       const int v = t + j * kWanThreads;
       if (v >= nvec) continue;
-      const int c0 = v * 8;
       float wv[8];
       if (!p.w) {
 #pragma unroll
@@ -604,17 +614,13 @@ wan_prologue_vec_kernel(const WanPrologueParams p) {
         }
         float o0 = y[0], o1 = y[1];
         if (rotate) {
-          const int jj = ((c0 + 2 * i) & 127) >> 1;          // complex index inside the head
-          const int row = jj < s0 ? fi : (jj < s0 + c3 ? hi_ : wi);
           if (p.hilo) {   // (re_hi, im_hi, re_lo, im_lo): the complex128 product rounded to fp32, on the FP32 pipe
-            const float4 fr = __ldg(reinterpret_cast<const float4*>(p.hilo) + static_cast<long long>(row) * 64 + jj);
-            o0 = comp_diff(y[0], fr.x, fr.z, y[1], fr.y, fr.w);          // a*re - b*im
-            o1 = comp_diff(y[0], fr.y, fr.w, -y[1], fr.x, fr.z);         // a*im + b*re
+            o0 = comp_diff(y[0], fr32[i].x, fr32[i].z, y[1], fr32[i].y, fr32[i].w);      // a*re - b*im
+            o1 = comp_diff(y[0], fr32[i].y, fr32[i].w, -y[1], fr32[i].x, fr32[i].z);     // a*im + b*re
           } else {
-            const double2 fr = __ldg(reinterpret_cast<const double2*>(p.freqs) + static_cast<long long>(row) * 64 + jj);
             const double a = static_cast<double>(y[0]), bb = static_cast<double>(y[1]);
-            o0 = static_cast<float>(a * fr.x - bb * fr.y);      // complex128 product, then .float()
-            o1 = static_cast<float>(a * fr.y + bb * fr.x);
+            o0 = static_cast<float>(a * fr64[i].x - bb * fr64[i].y);      // complex128 product, then .float()
+            o1 = static_cast<float>(a * fr64[i].y + bb * fr64[i].x);
           }
         }
         packed[i] = pack2<true>(o0, o1);
@@ -647,15 +653,14 @@ int wan_prologue_impl(const JengaWanPrologueArgs* a, cudaStream_t stream) {
   p.remap = reinterpret_cast<const long long*>(a->freq_remap);
   p.out = static_cast<uint16_t*>(a->out);
   p.hilo = a->freqs ? a->freqs_hilo : nullptr;
-  // Vector form when the caller supplied the fp32 split of the table (the fp64 pipe, not memory, bounds the
-  // rotation: scalar kernel 0.64-0.71 ms at Wan-14B size, vector kernel WITH fp64 1.0 ms) and rows are 16-byte
-  // addressable; JENGA_WAN_PROLOGUE=scalar forces the one-warp-per-token fp64 kernel, =vector64 the vector
-  // kernel with the fp64 rotation.
-  const int esz = p.x_f32 ? 4 : 2, wsz = p.w_f32 ? 4 : 2;
-  const char* wmode = std::getenv("JENGA_WAN_PROLOGUE");
+  // Default: the one-warp-per-token kernel (64 independent warps per SM; 0.64-0.72 ms at Wan-14B size = 0.37-0.49
+  // of the HBM peak).  JENGA_WAN_PROLOGUE=vector / vector64 select the experimental 128-threads-per-token kernel
+  // (row in registers, 16-byte accesses, four complex factors per token and thread; rotation on the FP32 pipe
+  // with the (hi, lo) table, or in fp64): same results (tests), but 0.90-0.98 ms — with 120 registers it runs 16
+  // warps per SM behind one block barrier per token pair and cannot overlap its load and compute phases.
   const bool want64 = wmode && wmode[0] == 'v' && wmode[1] == 'e' && std::strlen(wmode) >= 8;   // "vector64"
   if (want64) p.hilo = nullptr;
-  const bool vec_ok = !(wmode && wmode[0] == 's') && (p.hilo || !p.freqs || want64) && p.C % 8 == 0 && p.C / 8 <= 6 * kWanThreads &&
+  const bool vec_ok = (wmode && wmode[0] == 'v') && (p.hilo || !p.freqs || want64) && p.C % 8 == 0 && p.C / 8 <= 6 * kWanThreads &&
                       reinterpret_cast<uintptr_t>(p.x) % 16 == 0 && (p.sb * esz) % 16 == 0 && (p.ss * esz) % 16 == 0 &&
                       (!p.w || reinterpret_cast<uintptr_t>(p.w) % 16 == 0) && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
                       (!p.freqs || reinterpret_cast<uintptr_t>(p.freqs) % 16 == 0) &&
