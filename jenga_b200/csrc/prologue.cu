@@ -658,6 +658,8 @@ int wan_prologue_impl(const JengaWanPrologueArgs* a, cudaStream_t stream) {
   // (row in registers, 16-byte accesses, four complex factors per token and thread; rotation on the FP32 pipe
   // with the (hi, lo) table, or in fp64): same results (tests), but 0.90-0.98 ms — with 120 registers it runs 16
   // warps per SM behind one block barrier per token pair and cannot overlap its load and compute phases.
+  const int esz = p.x_f32 ? 4 : 2, wsz = p.w_f32 ? 4 : 2;
+  const char* wmode = std::getenv("JENGA_WAN_PROLOGUE");
   const bool want64 = wmode && wmode[0] == 'v' && wmode[1] == 'e' && std::strlen(wmode) >= 8;   // "vector64"
   if (want64) p.hilo = nullptr;
   const bool vec_ok = (wmode && wmode[0] == 'v') && (p.hilo || !p.freqs || want64) && p.C % 8 == 0 && p.C / 8 <= 6 * kWanThreads &&
